@@ -1,0 +1,153 @@
+/* libppv_b200 -- C ABI of the B200-native ppvector hot path.
+ *
+ * The reference (yeyupiaoling/VoiceprintRecognition-PaddlePaddle) has NO plugin / FFI interface:
+ * its boundary is the Python class surface.  Each entry point below names the reference
+ * call site it sits under (paths relative to the reference checkout); INTEGRATION.md shows the
+ * ctypes binding.  Conventions:
+ *   - plain pointers and sizes only; every tensor pointer is DEVICE memory owned by the caller,
+ *     row-major contiguous; the library never frees caller memory and allocates nothing per call
+ *     (per-call scratch is the caller's workspace);
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), no hidden sync;
+ *   - return value: 0 = PPV_OK, negative = error; ppv_last_error() gives the text;
+ *   - sm_100a only; there is no CPU fallback.
+ */
+#ifndef PPV_B200_H
+#define PPV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PPV_OK 0
+#define PPV_EINVAL (-1)       /* bad shape / null pointer / alignment */
+#define PPV_ECUDA (-2)        /* a CUDA runtime or driver call failed */
+#define PPV_EUNSUPPORTED (-3) /* configuration outside what the kernels implement */
+#define PPV_ESTATE (-4)       /* call order violated (e.g. forward before finalize) */
+
+/* Tensor-core contraction precision of the model GEMMs. */
+#define PPV_PREC_BF16X3 0 /* split-bf16, 3 MMAs per product: fp32-grade (parity mode, default) */
+#define PPV_PREC_BF16 1   /* single bf16 MMA: fast mode, ~1e-2 relative on embeddings */
+
+typedef struct ppv_fbank ppv_fbank_t;
+typedef struct ppv_model ppv_model_t;
+
+int ppv_version(void);
+/* Copies the calling thread's last error text (NUL-terminated) into buf; returns its length. */
+int ppv_last_error(char* buf, size_t n);
+/* Device properties the Python host needs without importing torch.cuda: SM count of the current device. */
+int ppv_device_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fbank front end.  Replaces ppvector/data_utils/featurizer.py:88-101 (KaldiFbank.forward ->
+ * paddleaudio.compliance.kaldi.fbank per utterance) and :33-60 (AudioFeaturizer.forward:
+ * transpose, subtract the time mean, optional tail mask).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int sample_rate;       /* 16000 */
+    int n_mels;            /* 80 (<= 128) */
+    float frame_length_ms; /* 25 */
+    float frame_shift_ms;  /* 10 */
+    float preemph;         /* 0.97 */
+    float low_freq;        /* 20 */
+    float high_freq;       /* 0 => Nyquist */
+    float log_floor;       /* 1.1920929e-07 (FLT_EPSILON) */
+} ppv_fbank_cfg;
+
+void ppv_fbank_default_cfg(ppv_fbank_cfg* cfg);
+int ppv_fbank_create(const ppv_fbank_cfg* cfg, ppv_fbank_t** out);
+int ppv_fbank_destroy(ppv_fbank_t* h);
+/* snip_edges frame count for L samples (0 if L < window). */
+int ppv_fbank_num_frames(const ppv_fbank_t* h, int L);
+int ppv_fbank_feature_dim(const ppv_fbank_t* h);
+/* wav [B,L] fp32 in [-1,1] -> out [B,T,n_mels] fp32, time-mean subtracted; if lens_ratio != NULL,
+ * frames t >= int(lens_ratio[b] * T) are zeroed AFTER the mean subtraction (featurizer.py:48-59). */
+int ppv_fbank_forward(ppv_fbank_t* h, const float* wav, const float* lens_ratio, int B, int L, float* out,
+                      void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Speaker-embedding model.  Replaces <Model>.forward, reached from
+ * ppvector/predict.py:228-233, :265-266 and ppvector/trainer.py:391-410 (eval mode, lengths=None).
+ * kind PPV_MODEL_ECAPA_TDNN: ppvector/models/ecapa_tdnn.py:245-276 with
+ * pooling.py:86-125 (ASP, global_context) and models/utils.py:65-148.
+ * ------------------------------------------------------------------------------------------- */
+#define PPV_MODEL_ECAPA_TDNN 1
+
+typedef struct {
+    int input_size;  /* 80 */
+    int embd_dim;    /* 192 */
+    int channels[5]; /* 512,512,512,512,1536 */
+    int kernel_sizes[5];
+    int dilations[5];
+    int attention_channels; /* 128 */
+    int res2net_scale;      /* 8 */
+    int se_channels;        /* 128 */
+    int precision;          /* PPV_PREC_* */
+} ppv_ecapa_cfg;
+
+void ppv_ecapa_default_cfg(ppv_ecapa_cfg* cfg);
+int ppv_model_create(int kind, const void* cfg, ppv_model_t** out);
+int ppv_model_destroy(ppv_model_t* h);
+/* Weights are COPIED (and re-laid-out for the tensor cores) at finalize; names and shapes are the
+ * reference state_dict's (e.g. "blocks.1.tdnn1.conv.conv.weight" [512,512,1], BatchNorm
+ * "weight"/"bias"/"_mean"/"_variance").  `data` is fp32, host or device memory. */
+int ppv_model_load_weight(ppv_model_t* h, const char* name, const float* data, const int64_t* shape, int ndim);
+int ppv_model_finalize(ppv_model_t* h);
+int ppv_model_set_precision(ppv_model_t* h, int precision);
+int ppv_model_embd_dim(const ppv_model_t* h);
+/* Scratch the caller must provide for a batch of B utterances of T frames (256-byte aligned). */
+size_t ppv_model_workspace_bytes(const ppv_model_t* h, int B, int T);
+/* feat [B,T,input_size] fp32 (AudioFeaturizer output) -> emb [B,embd_dim] fp32. */
+int ppv_model_forward(ppv_model_t* h, const float* feat, int B, int T, float* emb, void* ws, size_t ws_bytes,
+                      void* stream);
+/* Fused front end + model: wav [B,L] fp32 -> emb [B,embd_dim]; the Fbank features go straight into the
+ * first conv's operand layout and never exist as [B,T,F] fp32.  lens_ratio as ppv_fbank_forward. */
+int ppv_model_forward_wav(ppv_model_t* h, ppv_fbank_t* fb, const float* wav, const float* lens_ratio, int B, int L,
+                          float* emb, void* ws, size_t ws_bytes, void* stream);
+/* Debug / parity taps: copy an internal activation (valid frames only) to out as fp32.
+ * name in {"feat","blocks.0","blocks.1","blocks.2","blocks.3","mfa","asp"}; out is [B,T,C] ([B,C] for asp). */
+int ppv_model_read_tap(ppv_model_t* h, const char* name, float* out, size_t out_elems, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Cosine scoring.  Replaces ppvector/predict.py:279-283 (contrast), :173-187 (retrieval:
+ * sklearn cosine_similarity) and ppvector/trainer.py:416-423 (eval trial x enrol matrix).
+ * ------------------------------------------------------------------------------------------- */
+/* A [M,D], Bm [N,D] -> out [M,N], out[i,j] = <A_i,B_j> / (|A_i||B_j|).  ws: scratch of
+ * ppv_cosine_workspace_bytes(M,N,D) bytes, 256-byte aligned. */
+size_t ppv_cosine_workspace_bytes(int M, int N, int D);
+int ppv_cosine_matrix(const float* A, const float* Bm, int M, int N, int D, float* out, void* ws, size_t ws_bytes,
+                      void* stream);
+/* E [n,D], idx [P,2] int32 -> out [P]. */
+int ppv_cosine_pairlist(const float* E, const int32_t* idx, int64_t P, int n, int D, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Cosine classifier + AAMLoss.  Replaces ppvector/models/fc.py:41-53 (Cosine, num_blocks=0) and
+ * ppvector/loss/aamloss.py:28-46 (mean softmax-CE over scale * margin-adjusted cosines).
+ * W is [D,S] (Paddle layout, fc.py:31).  logits [B,S] receives the plain cosines
+ * (outputs['logits'] of the reference); loss is a device scalar.
+ * ------------------------------------------------------------------------------------------- */
+int ppv_aam_forward(const float* emb, const float* W, const int64_t* labels, int B, int D, int S, float margin,
+                    float scale, int easy_margin, float label_smoothing, float* logits, float* loss,
+                    void* ws, size_t ws_bytes, void* stream);
+size_t ppv_aam_workspace_bytes(int B, int D, int S);
+/* Gradients of the mean loss w.r.t. emb [B,D] and W [D,S]; uses logits from ppv_aam_forward and its ws. */
+int ppv_aam_backward(const float* emb, const float* W, const int64_t* labels, const float* logits, int B, int D,
+                     int S, float margin, float scale, int easy_margin, float label_smoothing, float* d_emb,
+                     float* d_W, void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Test hook for the tensor-core GEMM (not a reference entry point): out[M,N] = A[M,K] * W[N,K]^T
+ * (+bias, ReLU, BN affine as flagged) through the same tcgen05/TMA kernel the model uses.
+ * A, W, out fp32 device; ws >= ppv_gemm_test_workspace_bytes.
+ * ------------------------------------------------------------------------------------------- */
+size_t ppv_gemm_test_workspace_bytes(int M, int N, int K);
+int ppv_gemm_test(const float* A, const float* W, const float* bias, const float* bn_scale, const float* bn_shift,
+                  int relu, int M, int N, int K, int block_n, int precision, float* out, void* ws, size_t ws_bytes,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPV_B200_H */

@@ -1,0 +1,271 @@
+// extern "C" boundary of libppv_b200 (include/ppv_b200.h): argument checking, handle unwrapping, error text.
+// No exceptions cross this boundary; everything returns a status code.
+#include <string.h>
+
+#include <new>
+
+#include "common.h"
+
+namespace ppv {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+int device_sm_count() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return 148;
+    }
+    return n;
+}
+
+static int check_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return fail(PPV_ECUDA, "no CUDA device: libppv_b200 has no CPU fallback");
+    int major = 0, minor = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+    if (major != 10) return fail(PPV_EUNSUPPORTED, "libppv_b200 is built for sm_100a only (found sm_" + std::to_string(major * 10 + minor) + ")");
+    return PPV_OK;
+}
+
+}  // namespace ppv
+
+using namespace ppv;
+
+struct ppv_fbank {
+    Fbank* impl;
+};
+struct ppv_model {
+    int kind;
+    EcapaModel* ecapa;
+};
+
+#define PPV_GUARD_BEGIN try {
+#define PPV_GUARD_END                                                        \
+    }                                                                        \
+    catch (const std::bad_alloc&) { return fail(PPV_ECUDA, "host out of memory"); } \
+    catch (const std::exception& e) { return fail(PPV_EINVAL, std::string("exception: ") + e.what()); } \
+    catch (...) { return fail(PPV_EINVAL, "unknown exception"); }
+
+extern "C" {
+
+int ppv_version(void) { return 100; }
+
+int ppv_last_error(char* buf, size_t n) {
+    const std::string& e = g_last_error;
+    if (buf && n > 0) {
+        const size_t k = std::min(n - 1, e.size());
+        memcpy(buf, e.data(), k);
+        buf[k] = 0;
+    }
+    return int(e.size());
+}
+
+int ppv_device_sm_count(void) { return device_sm_count(); }
+
+// ---------------------------------------------------------------- fbank
+void ppv_fbank_default_cfg(ppv_fbank_cfg* c) {
+    if (!c) return;
+    c->sample_rate = 16000;
+    c->n_mels = 80;
+    c->frame_length_ms = 25.f;
+    c->frame_shift_ms = 10.f;
+    c->preemph = 0.97f;
+    c->low_freq = 20.f;
+    c->high_freq = 0.f;
+    c->log_floor = 1.1920928955078125e-07f;
+}
+
+int ppv_fbank_create(const ppv_fbank_cfg* cfg, ppv_fbank_t** out) {
+    PPV_GUARD_BEGIN
+    PPV_REQUIRE(cfg && out, "ppv_fbank_create: null argument");
+    int rc = check_device();
+    if (rc) return rc;
+    Fbank* impl = nullptr;
+    rc = fbank_create(cfg, &impl);
+    if (rc) return rc;
+    *out = new ppv_fbank{impl};
+    return PPV_OK;
+    PPV_GUARD_END
+}
+int ppv_fbank_destroy(ppv_fbank_t* h) {
+    if (!h) return PPV_OK;
+    fbank_destroy(h->impl);
+    delete h;
+    return PPV_OK;
+}
+int ppv_fbank_num_frames(const ppv_fbank_t* h, int L) { return h ? fbank_num_frames(h->impl, L) : 0; }
+int ppv_fbank_feature_dim(const ppv_fbank_t* h) { return h ? fbank_n_mels(h->impl) : 0; }
+
+int ppv_fbank_forward(ppv_fbank_t* h, const float* wav, const float* lens_ratio, int B, int L, float* out, void* stream) {
+    PPV_GUARD_BEGIN
+    PPV_REQUIRE(h && wav && out, "ppv_fbank_forward: null argument");
+    PPV_REQUIRE(B > 0 && L > 0, "ppv_fbank_forward: empty input");
+    // raw log-mel goes to `out`, then CMN is applied in place (each element is read and written by one thread)
+    return fbank_run(h->impl, wav, lens_ratio, B, L, out, out, Planes(), 0, 0, static_cast<cudaStream_t>(stream));
+    PPV_GUARD_END
+}
+
+// ---------------------------------------------------------------- model
+void ppv_ecapa_default_cfg(ppv_ecapa_cfg* c) {
+    if (!c) return;
+    c->input_size = 80;
+    c->embd_dim = 192;
+    const int ch[5] = {512, 512, 512, 512, 1536}, ks[5] = {5, 3, 3, 3, 1}, dl[5] = {1, 2, 3, 4, 1};
+    for (int i = 0; i < 5; ++i) {
+        c->channels[i] = ch[i];
+        c->kernel_sizes[i] = ks[i];
+        c->dilations[i] = dl[i];
+    }
+    c->attention_channels = 128;
+    c->res2net_scale = 8;
+    c->se_channels = 128;
+    c->precision = PPV_PREC_BF16X3;
+}
+
+int ppv_model_create(int kind, const void* cfg, ppv_model_t** out) {
+    PPV_GUARD_BEGIN
+    PPV_REQUIRE(cfg && out, "ppv_model_create: null argument");
+    if (kind != PPV_MODEL_ECAPA_TDNN) return fail(PPV_EUNSUPPORTED, "ppv_model_create: only PPV_MODEL_ECAPA_TDNN is implemented");
+    int rc = check_device();
+    if (rc) return rc;
+    EcapaModel* m = nullptr;
+    rc = ecapa_create(static_cast<const ppv_ecapa_cfg*>(cfg), &m);
+    if (rc) return rc;
+    *out = new ppv_model{kind, m};
+    return PPV_OK;
+    PPV_GUARD_END
+}
+int ppv_model_destroy(ppv_model_t* h) {
+    if (!h) return PPV_OK;
+    ecapa_destroy(h->ecapa);
+    delete h;
+    return PPV_OK;
+}
+int ppv_model_load_weight(ppv_model_t* h, const char* name, const float* data, const int64_t* shape, int ndim) {
+    PPV_GUARD_BEGIN
+    PPV_REQUIRE(h, "ppv_model_load_weight: null model");
+    return ecapa_load_weight(h->ecapa, name, data, shape, ndim);
+    PPV_GUARD_END
+}
+int ppv_model_finalize(ppv_model_t* h) {
+    PPV_GUARD_BEGIN
+    PPV_REQUIRE(h, "ppv_model_finalize: null model");
+    return ecapa_finalize(h->ecapa);
+    PPV_GUARD_END
+}
+int ppv_model_set_precision(ppv_model_t* h, int precision) {
+    PPV_REQUIRE(h, "ppv_model_set_precision: null model");
+    return ecapa_set_precision(h->ecapa, precision);
+}
+int ppv_model_embd_dim(const ppv_model_t* h) { return h ? ecapa_embd_dim(h->ecapa) : 0; }
+size_t ppv_model_workspace_bytes(const ppv_model_t* h, int B, int T) { return h ? ecapa_workspace_bytes(h->ecapa, B, T) : 0; }
+
+int ppv_model_forward(ppv_model_t* h, const float* feat, int B, int T, float* emb, void* ws, size_t ws_bytes, void* stream) {
+    PPV_GUARD_BEGIN
+    PPV_REQUIRE(h && feat && emb, "ppv_model_forward: null argument");
+    return ecapa_forward(h->ecapa, feat, nullptr, nullptr, nullptr, B, T, 0, emb, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+    PPV_GUARD_END
+}
+int ppv_model_forward_wav(ppv_model_t* h, ppv_fbank_t* fb, const float* wav, const float* lens_ratio, int B, int L, float* emb,
+                          void* ws, size_t ws_bytes, void* stream) {
+    PPV_GUARD_BEGIN
+    PPV_REQUIRE(h && fb && wav && emb, "ppv_model_forward_wav: null argument");
+    const int T = fbank_num_frames(fb->impl, L);
+    PPV_REQUIRE(T > 0, "ppv_model_forward_wav: waveform shorter than one frame");
+    return ecapa_forward(h->ecapa, nullptr, fb->impl, wav, lens_ratio, B, T, L, emb, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+    PPV_GUARD_END
+}
+int ppv_model_read_tap(ppv_model_t* h, const char* name, float* out, size_t out_elems, void* stream) {
+    PPV_GUARD_BEGIN
+    PPV_REQUIRE(h, "ppv_model_read_tap: null model");
+    return ecapa_read_tap(h->ecapa, name, out, out_elems, static_cast<cudaStream_t>(stream));
+    PPV_GUARD_END
+}
+
+// ---------------------------------------------------------------- cosine scoring
+size_t ppv_cosine_workspace_bytes(int M, int N, int D) { return cosine_workspace_bytes(M, N, D); }
+int ppv_cosine_matrix(const float* A, const float* Bm, int M, int N, int D, float* out, void* ws, size_t ws_bytes, void* stream) {
+    PPV_GUARD_BEGIN
+    int rc = check_device();
+    if (rc) return rc;
+    return cosine_matrix(A, Bm, M, N, D, out, ws, ws_bytes, PPV_PREC_BF16X3, static_cast<cudaStream_t>(stream));
+    PPV_GUARD_END
+}
+int ppv_cosine_pairlist(const float* E, const int32_t* idx, int64_t P, int n, int D, float* out, void* stream) {
+    PPV_GUARD_BEGIN
+    return cosine_pairlist(E, idx, P, n, D, out, static_cast<cudaStream_t>(stream));
+    PPV_GUARD_END
+}
+
+// ---------------------------------------------------------------- AAM head
+size_t ppv_aam_workspace_bytes(int B, int D, int S) { return aam_workspace_bytes(B, D, S); }
+int ppv_aam_forward(const float* emb, const float* W, const int64_t* labels, int B, int D, int S, float margin, float scale,
+                    int easy_margin, float label_smoothing, float* logits, float* loss, void* ws, size_t ws_bytes, void* stream) {
+    PPV_GUARD_BEGIN
+    return aam_forward(emb, W, labels, B, D, S, margin, scale, easy_margin, label_smoothing, logits, loss, ws, ws_bytes,
+                       static_cast<cudaStream_t>(stream));
+    PPV_GUARD_END
+}
+int ppv_aam_backward(const float* emb, const float* W, const int64_t* labels, const float* logits, int B, int D, int S, float margin,
+                     float scale, int easy_margin, float label_smoothing, float* d_emb, float* d_W, void* ws, size_t ws_bytes,
+                     void* stream) {
+    PPV_GUARD_BEGIN
+    return aam_backward(emb, W, labels, logits, B, D, S, margin, scale, easy_margin, label_smoothing, d_emb, d_W, ws, ws_bytes,
+                        static_cast<cudaStream_t>(stream));
+    PPV_GUARD_END
+}
+
+// ---------------------------------------------------------------- GEMM test hook
+static inline size_t au(size_t x, size_t a) { return (x + a - 1) / a * a; }
+size_t ppv_gemm_test_workspace_bytes(int M, int N, int K) {
+    const size_t Kp = au(size_t(K), 64);
+    return au(au(size_t(M), 128) * Kp * 4, 256) + au(au(size_t(N), 256) * Kp * 4, 256) + 256;
+}
+int ppv_gemm_test(const float* A, const float* W, const float* bias, const float* bn_scale, const float* bn_shift, int relu, int M,
+                  int N, int K, int block_n, int precision, float* out, void* ws, size_t ws_bytes, void* stream) {
+    PPV_GUARD_BEGIN
+    PPV_REQUIRE(A && W && out && ws, "ppv_gemm_test: null argument");
+    PPV_REQUIRE(ws_bytes >= ppv_gemm_test_workspace_bytes(M, N, K), "ppv_gemm_test: workspace too small");
+    int rc = check_device();
+    if (rc) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int Kp = int(au(size_t(K), 64));
+    Planes pa, pw;
+    pa.rows = int64_t(au(size_t(M), 128));
+    pa.ld = Kp;
+    pa.plane_stride = pa.rows * Kp;
+    pa.base = static_cast<__nv_bfloat16*>(ws);
+    pw.rows = int64_t(au(size_t(N), 256));
+    pw.ld = Kp;
+    pw.plane_stride = pw.rows * Kp;
+    pw.base = reinterpret_cast<__nv_bfloat16*>(static_cast<uint8_t*>(ws) + au(size_t(pa.plane_stride) * 4, 256));
+    PPV_CUDA_OK(cudaMemsetAsync(ws, 0, ppv_gemm_test_workspace_bytes(M, N, K), st));
+    rc = launch_f32_to_planes(A, M, K, pa, st);
+    if (rc) return rc;
+    rc = launch_f32_to_planes(W, N, K, pw, st);
+    if (rc) return rc;
+    GemmSource src{pa, 0, Kp, 0};
+    Epilogue ep;
+    ep.bias = bias;
+    ep.relu = relu;
+    ep.bn_scale = bn_scale;
+    ep.bn_shift = bn_shift;
+    ep.out_mode = OUT_F32;
+    ep.out = out;
+    ep.out_ld = N;
+    GemmParams gp;
+    rc = gemm_build(&gp, &src, 1, pw, M, N, ep, block_n);
+    if (rc) return rc;
+    return gemm_launch(gp, block_n, precision, device_sm_count(), st);
+    PPV_GUARD_END
+}
+
+}  // extern "C"

@@ -1,0 +1,161 @@
+// Shared host/device declarations for libppv_b200: status codes, error reporting, tensor views,
+// the GEMM launch parameters and the kernel launchers each .cu file exports to the others.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <string>
+
+#include "../../include/ppv_b200.h"
+
+namespace ppv {
+
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+
+#define PPV_CUDA_OK(expr)                                                                             \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess)                                                                        \
+            return ::ppv::fail(PPV_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));        \
+    } while (0)
+#define PPV_LAUNCH_OK(what)                                                                           \
+    do {                                                                                              \
+        cudaError_t _e = cudaGetLastError();                                                          \
+        if (_e != cudaSuccess) return ::ppv::fail(PPV_ECUDA, std::string(what) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+#define PPV_REQUIRE(cond, msg)                                     \
+    do {                                                           \
+        if (!(cond)) return ::ppv::fail(PPV_EINVAL, std::string(msg)); \
+    } while (0)
+
+// ---- activation storage ---------------------------------------------------------------------------
+// Activations between kernels are "split planes": two bf16 matrices hi/lo with x ~= hi + lo
+// (~2^-17 relative), row-major [2][rows][ld].  Rows are frames in the PADDED time layout
+//   row = b * Tp + P + t,  Tp = T + 2P,
+// so that a dilated conv tap is a plain row offset and the reflect padding of the reference's Conv1d
+// (ppvector/models/utils.py:79-93) is materialised as halo rows written by the producing epilogue.
+struct Planes {
+    __nv_bfloat16* base = nullptr;
+    int64_t rows = 0;
+    int ld = 0;                // elements per row
+    int64_t plane_stride = 0;  // elements between the hi and the lo plane
+    __host__ __device__ __nv_bfloat16* hi() const { return base; }
+    __host__ __device__ __nv_bfloat16* lo() const { return base + plane_stride; }
+};
+
+struct TimeLayout {  // padded time layout of a batch
+    int B = 0, T = 0, P = 0, Tp = 0;
+    int64_t rows() const { return int64_t(B) * Tp; }
+};
+
+// ---- GEMM -----------------------------------------------------------------------------------------
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_MAX_KSTEPS = 64;
+constexpr int GEMM_MAX_MAPS = 4;
+
+struct KStep {
+    int16_t map;      // which A tensor map
+    int16_t row_off;  // row offset (conv tap * dilation)
+    int32_t a_col;    // first column of the 64-wide K slice in that A tensor
+};
+
+enum OutMode : int { OUT_PLANES = 0, OUT_F32 = 1 };
+
+struct Epilogue {
+    const float* bias = nullptr;         // [N]
+    const float* rowgrp_bias = nullptr;  // [rows / rows_per_group][N]  (per-utterance bias)
+    const float* bn_scale = nullptr;     // [N]  y = y * scale + shift  (BatchNorm eval, after ReLU)
+    const float* bn_shift = nullptr;     // [N]
+    int relu = 0;
+    int tanh_ = 0;
+    int out_mode = OUT_PLANES;
+    void* out = nullptr;            // Planes base (bf16) or float*
+    int64_t out_ld = 0;             // elements
+    int64_t out_plane_stride = 0;   // elements (OUT_PLANES)
+    int out_col0 = 0;
+    // row validity: Tp == 0 -> rows [0, M) are all valid (plain matrix); else padded time layout.
+    int Tp = 0, P = 0, T = 0;
+    int halo = 0;  // also write the reflect halo rows (output feeds a dilated conv)
+    int f32_vec_ok = 0;  // set by gemm_build: OUT_F32 rows are 16-byte aligned
+};
+
+struct GemmParams {
+    CUtensorMap mapA[GEMM_MAX_MAPS];
+    CUtensorMap mapB;
+    KStep ksteps[GEMM_MAX_KSTEPS];
+    int num_ksteps;
+    int M, N;
+    int m_tiles, n_tiles;
+    Epilogue epi;
+};
+
+struct GemmSource {
+    Planes t;
+    int col0;     // first column
+    int ncols;    // multiple of 64
+    int row_off;  // tap offset in rows
+};
+
+// Precision of the tensor-core contraction.
+//   PPV_PREC_BF16X3: A_hi*B_hi + A_lo*B_hi + A_hi*B_lo  (fp32-grade, ~2^-16 relative per product)
+//   PPV_PREC_BF16  : A_hi*B_hi only
+int gemm_build(GemmParams* gp, const GemmSource* srcs, int nsrc, const Planes& W, int M, int N, const Epilogue& epi,
+               int BN);
+int gemm_launch(const GemmParams& gp, int BN, int precision, int num_sms, cudaStream_t stream);
+int gemm_max_smem_setup();
+
+// ---- other kernels (elementwise.cu) ---------------------------------------------------------------
+int launch_pack_features(const float* feat, int B, int T, int F, const Planes& out, int P, int Tp, cudaStream_t st);
+int launch_colstats(const Planes& x, int col0, int C, int B, int T, int P, int Tp, int mode, float eps, float* out_f32,
+                    const Planes& out_pl, cudaStream_t st);
+int launch_se_excite(const float* mean, const float* W1, const float* b1, const float* W2, const float* b2, int B, int C,
+                     int S, float* scale, cudaStream_t st);
+int launch_se_scale_res(const Planes& z, const float* scale, const Planes& res, int rc0, const Planes& out, int oc0, int C,
+                        int Tp, int64_t rows, int num_sms, cudaStream_t st);
+int launch_asp_pool(const float* logits, int64_t lg_ld, const Planes& x, int C, int B, int T, int P, int Tp, float eps,
+                    const float* bn_scale, const float* bn_shift, const Planes& out_pl, float* out_raw, cudaStream_t st);
+int launch_planes_to_f32(const Planes& x, int col0, int C, int B, int T, int P, int Tp, float* out, cudaStream_t st);
+int launch_f32_to_planes(const float* src, int64_t rows, int cols, const Planes& out, cudaStream_t st);
+
+// ---- fbank.cu ---------------------------------------------------------------------------------------
+struct Fbank;
+int fbank_create(const ppv_fbank_cfg* cfg, Fbank** out);
+void fbank_destroy(Fbank* h);
+int fbank_num_frames(const Fbank* h, int L);
+int fbank_n_mels(const Fbank* h);
+int fbank_run(Fbank* h, const float* wav, const float* lens_ratio, int B, int L, float* raw, float* out_f32,
+              const Planes& out_pl, int P, int Tp, cudaStream_t st);
+
+// ---- ecapa.cu ---------------------------------------------------------------------------------------
+struct EcapaModel;
+int ecapa_create(const ppv_ecapa_cfg* cfg, EcapaModel** out);
+void ecapa_destroy(EcapaModel* m);
+int ecapa_load_weight(EcapaModel* m, const char* name, const float* data, const int64_t* shape, int ndim);
+int ecapa_finalize(EcapaModel* m);
+int ecapa_set_precision(EcapaModel* m, int precision);
+int ecapa_embd_dim(const EcapaModel* m);
+size_t ecapa_workspace_bytes(const EcapaModel* m, int B, int T);
+int ecapa_forward(EcapaModel* m, const float* feat, Fbank* fb, const float* wav, const float* lens_ratio, int B, int T, int L,
+                  float* emb, void* ws, size_t ws_bytes, cudaStream_t st);
+int ecapa_read_tap(EcapaModel* m, const char* name, float* out, size_t out_elems, cudaStream_t st);
+
+// ---- cosine.cu / aam.cu -----------------------------------------------------------------------------
+size_t cosine_workspace_bytes(int M, int N, int D);
+int cosine_matrix(const float* A, const float* Bm, int M, int N, int D, float* out, void* ws, size_t ws_bytes, int precision,
+                  cudaStream_t st);
+int cosine_pairlist(const float* E, const int32_t* idx, int64_t P, int n, int D, float* out, cudaStream_t st);
+size_t aam_workspace_bytes(int B, int D, int S);
+int aam_forward(const float* emb, const float* W, const int64_t* labels, int B, int D, int S, float margin, float scale,
+                int easy_margin, float label_smoothing, float* logits, float* loss, void* ws, size_t ws_bytes, cudaStream_t st);
+int aam_backward(const float* emb, const float* W, const int64_t* labels, const float* logits, int B, int D, int S, float margin,
+                 float scale, int easy_margin, float label_smoothing, float* d_emb, float* d_W, void* ws, size_t ws_bytes,
+                 cudaStream_t st);
+
+int device_sm_count();
+
+}  // namespace ppv

@@ -1,0 +1,314 @@
+// HBM-bound kernels between the tensor-core GEMMs of the ECAPA-TDNN path:
+//   pack_features   [B,T,F] fp32 -> split-bf16 planes in the padded time layout (+ reflect halo)
+//   se_squeeze      SEBlock mean over time            (ppvector/models/ecapa_tdnn.py:69-78)
+//   se_excite       SEBlock conv1-ReLU-conv2-sigmoid  (ecapa_tdnn.py:79-80)
+//   se_scale_res    s * x + residual                  (ecapa_tdnn.py:82, :142)
+//   asp_global      global mean / std of ASP          (ppvector/models/pooling.py:89-92, 102-104)
+//   asp_pool        masked softmax over time + weighted mean / std + asp_bn (pooling.py:115-123,
+//                   ecapa_tdnn.py:271)
+//   planes_to_f32   debug taps
+// Layout: rows are frames (padded time layout, common.h), channels are contiguous, so a warp reads
+// 32 x bf16x2 = 128 contiguous bytes per row; reductions over time keep per-thread fp32 partials and
+// finish through shared memory in a fixed order (deterministic).
+#include "common.h"
+#include "ptx.cuh"
+
+namespace ppv {
+
+__device__ __forceinline__ float2 ld_split2(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int64_t off) {
+    const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(hi + off);
+    const __nv_bfloat162 l = *reinterpret_cast<const __nv_bfloat162*>(lo + off);
+    const float2 hf = __bfloat1622float2(h);
+    const float2 lf = __bfloat1622float2(l);
+    return make_float2(hf.x + lf.x, hf.y + lf.y);
+}
+__device__ __forceinline__ void st_split2(__nv_bfloat16* hi, __nv_bfloat16* lo, int64_t off, float a, float b) {
+    __nv_bfloat16 h0, l0, h1, l1;
+    split_bf16(a, h0, l0);
+    split_bf16(b, h1, l1);
+    *reinterpret_cast<uint32_t*>(hi + off) = pack_bf16x2(h0, h1);
+    *reinterpret_cast<uint32_t*>(lo + off) = pack_bf16x2(l0, l1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// pack_features: one warp per frame row; channels >= F are zero-filled (K padding of the first conv).
+__global__ void pack_features_kernel(const float* __restrict__ feat, int B, int T, int F, Planes out, int P, int Tp) {
+    const int warps_per_block = blockDim.x >> 5;
+    const int64_t frame = int64_t(blockIdx.x) * warps_per_block + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (frame >= int64_t(B) * T) return;
+    const int b = int(frame / T);
+    const int t = int(frame - int64_t(b) * T);
+    const float* src = feat + frame * F;
+    const int64_t row = int64_t(b) * Tp + P + t;
+    int64_t rows[3] = {row, -1, -1};
+    if (t >= 1 && t <= P) rows[1] = row - 2 * t;
+    const int u = T - 1 - t;
+    if (u >= 1 && u <= P) rows[2] = row + 2 * u;
+    for (int c = 2 * lane; c < out.ld; c += 64) {
+        const float a = (c < F) ? src[c] : 0.f;
+        const float bb = (c + 1 < F) ? src[c + 1] : 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (rows[k] >= 0) st_split2(out.hi(), out.lo(), rows[k] * out.ld + c, a, bb);
+    }
+}
+
+int launch_pack_features(const float* feat, int B, int T, int F, const Planes& out, int P, int Tp, cudaStream_t st) {
+    const int64_t frames = int64_t(B) * T;
+    const int wpb = 8;
+    pack_features_kernel<<<unsigned((frames + wpb - 1) / wpb), wpb * 32, 0, st>>>(feat, B, T, F, out, P, Tp);
+    PPV_LAUNCH_OK("pack_features_kernel");
+    return PPV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Column statistics over the valid frames of one utterance.  Block = (utterance b, 64-channel slab),
+// 256 threads = 8 warps; warp w takes frames w, w+8, ...; lane l takes channels 2l, 2l+1 of the slab.
+constexpr int STAT_WARPS = 8;
+
+__device__ __forceinline__ float2 block_colsum(float2 v, float2 (*s_part)[32], int warp, int lane) {
+    s_part[warp][lane] = v;
+    __syncthreads();
+    float2 r = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int w = 0; w < STAT_WARPS; ++w) {
+        r.x += s_part[w][lane].x;
+        r.y += s_part[w][lane].y;
+    }
+    __syncthreads();
+    return r;
+}
+
+// mode 0: mean only -> out_f32[b, C]            (SE squeeze)
+// mode 1: mean and std = sqrt(clip(sum((x-mean)^2)/T, eps)) -> planes [B, 2C] (mean | std)  (ASP global context)
+__global__ void __launch_bounds__(STAT_WARPS * 32)
+    colstats_kernel(Planes x, int col0, int C, int T, int P, int Tp, int mode, float eps, float* __restrict__ out_f32,
+                    Planes out_pl) {
+    __shared__ float2 s_part[STAT_WARPS][32];
+    const int b = blockIdx.y;
+    const int c = col0 + blockIdx.x * 64 + 2 * (threadIdx.x & 31);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row0 = int64_t(b) * Tp + P;
+    float2 acc = make_float2(0.f, 0.f);
+    for (int t = warp; t < T; t += STAT_WARPS) {
+        const float2 v = ld_split2(x.hi(), x.lo(), (row0 + t) * x.ld + c);
+        acc.x += v.x;
+        acc.y += v.y;
+    }
+    float2 sum = block_colsum(acc, s_part, warp, lane);
+    const float inv = 1.f / float(T);
+    const float2 mean = make_float2(sum.x * inv, sum.y * inv);
+    const int cc = blockIdx.x * 64 + 2 * lane;  // channel index relative to col0
+    if (mode == 0) {
+        if (warp == 0) *reinterpret_cast<float2*>(out_f32 + int64_t(b) * C + cc) = mean;
+        return;
+    }
+    acc = make_float2(0.f, 0.f);
+    for (int t = warp; t < T; t += STAT_WARPS) {
+        const float2 v = ld_split2(x.hi(), x.lo(), (row0 + t) * x.ld + c);
+        const float dx = v.x - mean.x, dy = v.y - mean.y;
+        acc.x += dx * dx;
+        acc.y += dy * dy;
+    }
+    sum = block_colsum(acc, s_part, warp, lane);
+    if (warp == 0) {
+        const float sx = sqrtf(fmaxf(sum.x * inv, eps)), sy = sqrtf(fmaxf(sum.y * inv, eps));
+        st_split2(out_pl.hi(), out_pl.lo(), int64_t(b) * out_pl.ld + cc, mean.x, mean.y);
+        st_split2(out_pl.hi(), out_pl.lo(), int64_t(b) * out_pl.ld + C + cc, sx, sy);
+    }
+}
+
+int launch_colstats(const Planes& x, int col0, int C, int B, int T, int P, int Tp, int mode, float eps, float* out_f32,
+                    const Planes& out_pl, cudaStream_t st) {
+    PPV_REQUIRE(C % 64 == 0, "colstats: C must be a multiple of 64");
+    dim3 grid(C / 64, B);
+    colstats_kernel<<<grid, STAT_WARPS * 32, 0, st>>>(x, col0, C, T, P, Tp, mode, eps, out_f32, out_pl);
+    PPV_LAUNCH_OK("colstats_kernel");
+    return PPV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SE excitation: s = sigmoid(W2 relu(W1 m + b1) + b2), one block per utterance.  W1 [S,C], W2 [C,S] fp32.
+__global__ void __launch_bounds__(256)
+    se_excite_kernel(const float* __restrict__ mean, const float* __restrict__ W1, const float* __restrict__ b1,
+                     const float* __restrict__ W2, const float* __restrict__ b2, int C, int S, float* __restrict__ scale) {
+    extern __shared__ float sm[];
+    float* s_m = sm;      // [C]
+    float* s_h = sm + C;  // [S]
+    const int b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) s_m[i] = mean[int64_t(b) * C + i];
+    __syncthreads();
+    for (int j = warp; j < S; j += 8) {
+        const float* w = W1 + int64_t(j) * C;
+        float a = 0.f;
+        for (int i = lane; i < C; i += 32) a = fmaf(w[i], s_m[i], a);
+        a = warp_sum(a);
+        if (lane == 0) s_h[j] = fmaxf(a + b1[j], 0.f);
+    }
+    __syncthreads();
+    for (int j = warp; j < C; j += 8) {
+        const float* w = W2 + int64_t(j) * S;
+        float a = 0.f;
+        for (int i = lane; i < S; i += 32) a = fmaf(w[i], s_h[i], a);
+        a = warp_sum(a);
+        if (lane == 0) scale[int64_t(b) * C + j] = 1.f / (1.f + expf(-(a + b2[j])));
+    }
+}
+
+int launch_se_excite(const float* mean, const float* W1, const float* b1, const float* W2, const float* b2, int B, int C,
+                     int S, float* scale, cudaStream_t st) {
+    se_excite_kernel<<<B, 256, (C + S) * sizeof(float), st>>>(mean, W1, b1, W2, b2, C, S, scale);
+    PPV_LAUNCH_OK("se_excite_kernel");
+    return PPV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// out[r, oc0 + c] = scale[b(r), c] * z[r, c] + res[r, rc0 + c]   for every row of the padded layout.
+__global__ void __launch_bounds__(256)
+    se_scale_res_kernel(Planes z, const float* __restrict__ scale, Planes res, int rc0, Planes out, int oc0, int C, int Tp,
+                        int64_t rows) {
+    const int pairs = C >> 1;
+    const int64_t total = rows * pairs;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t r = i / pairs;
+        const int c = int(i - r * pairs) * 2;
+        const int b = int(r / Tp);
+        const float2 zv = ld_split2(z.hi(), z.lo(), r * z.ld + c);
+        const float2 rv = ld_split2(res.hi(), res.lo(), r * res.ld + rc0 + c);
+        const float2 sv = *reinterpret_cast<const float2*>(scale + int64_t(b) * C + c);
+        st_split2(out.hi(), out.lo(), r * out.ld + oc0 + c, fmaf(sv.x, zv.x, rv.x), fmaf(sv.y, zv.y, rv.y));
+    }
+}
+
+int launch_se_scale_res(const Planes& z, const float* scale, const Planes& res, int rc0, const Planes& out, int oc0, int C,
+                        int Tp, int64_t rows, int num_sms, cudaStream_t st) {
+    const int64_t total = rows * (C / 2);
+    const int64_t want = (total + 255) / 256;
+    const int grid = int(std::min<int64_t>(want, int64_t(num_sms) * 16));
+    se_scale_res_kernel<<<grid, 256, 0, st>>>(z, scale, res, rc0, out, oc0, C, Tp, rows);
+    PPV_LAUNCH_OK("se_scale_res_kernel");
+    return PPV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ASP pooling (lengths = None): per (utterance, channel)
+//   a_t = softmax_t(logit_t);  mean = sum a_t x_t;  std = sqrt(clip(sum a_t (x_t - mean)^2, eps))
+// then asp_bn (eval affine) on the concatenated [mean | std] -> split planes [B, 2C] feeding the fc GEMM.
+__global__ void __launch_bounds__(STAT_WARPS * 32)
+    asp_pool_kernel(const float* __restrict__ logits, int64_t lg_ld, Planes x, int C, int T, int P, int Tp, float eps,
+                    const float* __restrict__ bn_scale, const float* __restrict__ bn_shift, Planes out_pl,
+                    float* __restrict__ out_raw) {
+    __shared__ float2 s_part[STAT_WARPS][32];
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * 64 + 2 * lane;
+    const int64_t row0 = int64_t(b) * Tp + P;
+    // pass 1: max
+    float2 mx = make_float2(-INFINITY, -INFINITY);
+    for (int t = warp; t < T; t += STAT_WARPS) {
+        const float2 l = *reinterpret_cast<const float2*>(logits + (row0 + t) * lg_ld + c);
+        mx.x = fmaxf(mx.x, l.x);
+        mx.y = fmaxf(mx.y, l.y);
+    }
+    s_part[warp][lane] = mx;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < STAT_WARPS; ++w) {
+        mx.x = fmaxf(mx.x, s_part[w][lane].x);
+        mx.y = fmaxf(mx.y, s_part[w][lane].y);
+    }
+    __syncthreads();
+    // pass 2: sum e, sum e x
+    float2 se = make_float2(0.f, 0.f), sx = make_float2(0.f, 0.f);
+    for (int t = warp; t < T; t += STAT_WARPS) {
+        const float2 l = *reinterpret_cast<const float2*>(logits + (row0 + t) * lg_ld + c);
+        const float2 v = ld_split2(x.hi(), x.lo(), (row0 + t) * x.ld + c);
+        const float ex = expf(l.x - mx.x), ey = expf(l.y - mx.y);
+        se.x += ex;
+        se.y += ey;
+        sx.x = fmaf(ex, v.x, sx.x);
+        sx.y = fmaf(ey, v.y, sx.y);
+    }
+    se = block_colsum(se, s_part, warp, lane);
+    sx = block_colsum(sx, s_part, warp, lane);
+    const float2 inv = make_float2(1.f / se.x, 1.f / se.y);
+    const float2 mean = make_float2(sx.x * inv.x, sx.y * inv.y);
+    // pass 3: weighted variance around the mean
+    float2 sv = make_float2(0.f, 0.f);
+    for (int t = warp; t < T; t += STAT_WARPS) {
+        const float2 l = *reinterpret_cast<const float2*>(logits + (row0 + t) * lg_ld + c);
+        const float2 v = ld_split2(x.hi(), x.lo(), (row0 + t) * x.ld + c);
+        const float ax = expf(l.x - mx.x) * inv.x, ay = expf(l.y - mx.y) * inv.y;
+        const float dx = v.x - mean.x, dy = v.y - mean.y;
+        sv.x = fmaf(ax, dx * dx, sv.x);
+        sv.y = fmaf(ay, dy * dy, sv.y);
+    }
+    sv = block_colsum(sv, s_part, warp, lane);
+    if (warp == 0) {
+        const float stdx = sqrtf(fmaxf(sv.x, eps)), stdy = sqrtf(fmaxf(sv.y, eps));
+        if (out_raw) {
+            *reinterpret_cast<float2*>(out_raw + int64_t(b) * 2 * C + c) = mean;
+            *reinterpret_cast<float2*>(out_raw + int64_t(b) * 2 * C + C + c) = make_float2(stdx, stdy);
+        }
+        const float2 s0 = *reinterpret_cast<const float2*>(bn_scale + c), h0 = *reinterpret_cast<const float2*>(bn_shift + c);
+        const float2 s1 = *reinterpret_cast<const float2*>(bn_scale + C + c),
+                     h1 = *reinterpret_cast<const float2*>(bn_shift + C + c);
+        st_split2(out_pl.hi(), out_pl.lo(), int64_t(b) * out_pl.ld + c, fmaf(mean.x, s0.x, h0.x), fmaf(mean.y, s0.y, h0.y));
+        st_split2(out_pl.hi(), out_pl.lo(), int64_t(b) * out_pl.ld + C + c, fmaf(stdx, s1.x, h1.x), fmaf(stdy, s1.y, h1.y));
+    }
+}
+
+int launch_asp_pool(const float* logits, int64_t lg_ld, const Planes& x, int C, int B, int T, int P, int Tp, float eps,
+                    const float* bn_scale, const float* bn_shift, const Planes& out_pl, float* out_raw, cudaStream_t st) {
+    PPV_REQUIRE(C % 64 == 0, "asp_pool: C must be a multiple of 64");
+    dim3 grid(C / 64, B);
+    asp_pool_kernel<<<grid, STAT_WARPS * 32, 0, st>>>(logits, lg_ld, x, C, T, P, Tp, eps, bn_scale, bn_shift, out_pl, out_raw);
+    PPV_LAUNCH_OK("asp_pool_kernel");
+    return PPV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// planes (padded layout, valid frames) -> fp32 [B,T,C]   (debug taps / tests)
+__global__ void planes_to_f32_kernel(Planes x, int col0, int C, int B, int T, int P, int Tp, float* __restrict__ out) {
+    const int64_t total = int64_t(B) * T * C;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+        const int c = int(i % C);
+        const int64_t f = i / C;
+        const int b = int(f / T), t = int(f % T);
+        const int64_t off = (int64_t(b) * Tp + P + t) * x.ld + col0 + c;
+        out[i] = __bfloat162float(x.hi()[off]) + __bfloat162float(x.lo()[off]);
+    }
+}
+
+int launch_planes_to_f32(const Planes& x, int col0, int C, int B, int T, int P, int Tp, float* out, cudaStream_t st) {
+    const int64_t total = int64_t(B) * T * C;
+    const int grid = int(std::min<int64_t>((total + 255) / 256, 148 * 32));
+    planes_to_f32_kernel<<<grid, 256, 0, st>>>(x, col0, C, B, T, P, Tp, out);
+    PPV_LAUNCH_OK("planes_to_f32_kernel");
+    return PPV_OK;
+}
+
+// fp32 row-major [rows, cols] -> split planes (test hook + weight upload helper)
+__global__ void f32_to_planes_kernel(const float* __restrict__ src, int64_t rows, int cols, Planes out) {
+    const int64_t total = rows * cols;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t r = i / cols;
+        const int c = int(i - r * cols);
+        __nv_bfloat16 h, l;
+        split_bf16(src[i], h, l);
+        out.hi()[r * out.ld + c] = h;
+        out.lo()[r * out.ld + c] = l;
+    }
+}
+
+int launch_f32_to_planes(const float* src, int64_t rows, int cols, const Planes& out, cudaStream_t st) {
+    const int64_t total = rows * cols;
+    const int grid = int(std::min<int64_t>((total + 255) / 256, 148 * 32));
+    f32_to_planes_kernel<<<grid, 256, 0, st>>>(src, rows, cols, out);
+    PPV_LAUNCH_OK("f32_to_planes_kernel");
+    return PPV_OK;
+}
+
+}  // namespace ppv

@@ -1,0 +1,410 @@
+// Gather-GEMM on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), the contraction behind every
+// Conv1d / Linear of the ppvector hot path (reference: ppvector/models/utils.py:65-77 Conv1d.forward,
+// reached from TDNNBlock utils.py:147, Res2NetBlock ecapa_tdnn.py:36-47, ASP pooling.py:107, fc).
+//
+//   out[r, n] = epilogue( sum_s  A_{map(s)}[r + row_off(s), a_col(s) : a_col(s)+64] . W[n, 64 s : 64 s + 64] )
+//
+// A "k-step" s is one 64-wide K slice: a conv tap is a row offset in the padded time layout, a channel
+// concat is a different source tensor, `x_i + y_{i-1}` (Res2Net) is two sources sharing the same weights.
+// Operands are split-bf16 planes (hi, lo); PPV_PREC_BF16X3 issues hi*hi + lo*hi + hi*lo into one fp32
+// TMEM accumulator (fp32-grade), PPV_PREC_BF16 issues hi*hi only.
+//
+// Warp roles (256 threads, 1 CTA / SM, persistent over tiles):
+//   warp 0    TMA producer  : cp.async.bulk.tensor 3-D tiles (SWIZZLE_128B) into a STAGES-deep smem ring
+//   warp 1    MMA issuer    : one lane issues tcgen05.mma (M=128, N=BN, K=16) ; tcgen05.commit frees the slot
+//   warp 2    TMEM allocator
+//   warps 4-7 epilogue      : tcgen05.ld 32 columns at a time -> bias / ReLU / BN affine / tanh ->
+//                             split-bf16 (or fp32) stores incl. the reflect-halo rows
+// TMEM holds two BN-column fp32 accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace ppv {
+
+template <int BN, int NSPLIT>
+struct GemmCfg {
+    static constexpr int NA = (NSPLIT == 3) ? 2 : 1;  // A tiles per stage (hi[, lo])
+    static constexpr int NB = NA;
+    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
+    static constexpr int B_BYTES = BN * GEMM_BK * 2;
+    static constexpr int STAGE_BYTES = NA * A_BYTES + NB * B_BYTES;
+    static constexpr int VEC_BYTES = 3 * BN * 4;  // bias / bn_scale / bn_shift slices
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int MAX_SMEM = 232448;  // 227 KB
+    static constexpr int STAGES_RAW = (MAX_SMEM - 1024 - VEC_BYTES - BAR_BYTES) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + VEC_BYTES + BAR_BYTES;
+    static constexpr int TMEM_COLS = 2 * BN;  // 128 / 256 / 512: power of two >= 32
+    static_assert(STAGES >= 2, "need at least a double buffer");
+    static_assert(BN == 64 || BN == 128 || BN == 256, "BN");
+};
+
+template <int BN, int NSPLIT>
+__global__ void __launch_bounds__(256, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams gp) {
+    using Cfg = GemmCfg<BN, NSPLIT>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment.
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t tiles_base = smem_base;
+    float* s_vec = reinterpret_cast<float*>(smem_gen + STAGES * Cfg::STAGE_BYTES);
+    const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES + Cfg::VEC_BYTES;
+    // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+    volatile uint32_t* tmem_slot_gen =
+        reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + Cfg::VEC_BYTES + 8 * (2 * STAGES + 4));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < GEMM_MAX_MAPS; ++i) prefetch_tmap(&gp.mapA[i]);
+        prefetch_tmap(&gp.mapB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 128);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    const int num_tiles = gp.m_tiles * gp.n_tiles;
+    const int nk = gp.num_ksteps;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m0 = (tile / gp.n_tiles) * GEMM_BM;
+            const int n0 = (tile % gp.n_tiles) * BN;
+            for (int s = 0; s < nk; ++s) {
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                if (lane == 0) {
+                    const KStep ks = gp.ksteps[s];
+                    const uint32_t sa = tiles_base + stage * Cfg::STAGE_BYTES;
+                    const uint32_t sb = sa + Cfg::NA * Cfg::A_BYTES;
+                    const uint32_t fb = full_bar(stage);
+                    mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
+                    const CUtensorMap* ma = &gp.mapA[ks.map];
+#pragma unroll
+                    for (int p = 0; p < Cfg::NA; ++p)
+                        tma_load_3d(sa + p * Cfg::A_BYTES, ma, fb, ks.a_col, m0 + ks.row_off, p);
+#pragma unroll
+                    for (int p = 0; p < Cfg::NB; ++p)
+                        tma_load_3d(sb + p * Cfg::B_BYTES, &gp.mapB, fb, s * GEMM_BK, n0, p);
+                }
+                __syncwarp();
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue drained this accumulator
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int s = 0; s < nk; ++s) {
+                mbar_wait(full_bar(stage), phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = tiles_base + stage * Cfg::STAGE_BYTES;
+                    const uint32_t sb = sa + Cfg::NA * Cfg::A_BYTES;
+                    const uint64_t a_hi = make_sw128_kmajor_desc(sa);
+                    const uint64_t b_hi = make_sw128_kmajor_desc(sb);
+                    // K advance inside the 128-byte swizzle atom: +32 B (16 bf16) per UMMA_K => +2 in desc.lo
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; ++k)
+                        umma_bf16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (s > 0 || k > 0) ? 1u : 0u);
+                    if (NSPLIT == 3) {
+                        const uint64_t a_lo = make_sw128_kmajor_desc(sa + Cfg::A_BYTES);
+                        const uint64_t b_lo = make_sw128_kmajor_desc(sb + Cfg::B_BYTES);
+#pragma unroll
+                        for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+#pragma unroll
+                        for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+                    }
+                    umma_commit(empty_bar(stage));                   // smem slot free when these MMAs retire
+                    if (s == nk - 1) umma_commit(tfull_bar(acc));   // accumulator complete
+                }
+                __syncwarp();
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const Epilogue& ep = gp.epi;
+        const int q = warp & 3;             // TMEM lane quarter this warp may read
+        const int etid = threadIdx.x - 128;  // 0..127
+        float* s_bias = s_vec;
+        float* s_scale = s_vec + BN;
+        float* s_shift = s_vec + 2 * BN;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m0 = (tile / gp.n_tiles) * GEMM_BM;
+            const int n0 = (tile % gp.n_tiles) * BN;
+            // stage the per-column vectors of this N slice
+            named_bar_sync(1, 128);
+            for (int i = etid; i < BN; i += 128) {
+                const int n = n0 + i;
+                const bool ok = n < gp.N;
+                s_bias[i] = (ep.bias && ok) ? __ldg(ep.bias + n) : 0.f;
+                s_scale[i] = (ep.bn_scale && ok) ? __ldg(ep.bn_scale + n) : 1.f;
+                s_shift[i] = (ep.bn_shift && ok) ? __ldg(ep.bn_shift + n) : 0.f;
+            }
+            named_bar_sync(1, 128);
+
+            // row bookkeeping
+            const int64_t row = int64_t(m0) + q * 32 + lane;
+            bool valid = row < gp.M;
+            int64_t mirror_a = -1, mirror_b = -1;
+            int64_t grp = 0;
+            if (ep.Tp > 0) {
+                grp = row / ep.Tp;
+                const int t = int(row - grp * ep.Tp) - ep.P;
+                valid = valid && t >= 0 && t < ep.T;
+                if (ep.halo && valid) {
+                    if (t >= 1 && t <= ep.P) mirror_a = row - 2 * t;
+                    const int u = ep.T - 1 - t;  // distance from the last frame
+                    if (u >= 1 && u <= ep.P) mirror_b = row + 2 * u;
+                }
+            }
+
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the divergent stores
+                tmem_ld32(t_addr + c * 32, v);
+                tmem_ld_wait();
+                const int col = n0 + c * 32;
+                if (!valid || col >= gp.N) continue;
+                float x[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + s_bias[c * 32 + j];
+                if (ep.rowgrp_bias) {
+                    const float4* rg = reinterpret_cast<const float4*>(ep.rowgrp_bias + grp * gp.N + col);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b4 = __ldg(rg + j);
+                        x[4 * j + 0] += b4.x;
+                        x[4 * j + 1] += b4.y;
+                        x[4 * j + 2] += b4.z;
+                        x[4 * j + 3] += b4.w;
+                    }
+                }
+                if (ep.relu) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+                }
+                if (ep.bn_scale) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] = fmaf(x[j], s_scale[c * 32 + j], s_shift[c * 32 + j]);
+                }
+                if (ep.tanh_) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] = tanhf(x[j]);
+                }
+                if (ep.out_mode == OUT_F32) {
+                    float* dstf = static_cast<float*>(ep.out) + row * ep.out_ld + ep.out_col0 + col;
+                    if (ep.f32_vec_ok && col + 32 <= gp.N) {
+                        float4* dst = reinterpret_cast<float4*>(dstf);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) dst[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+                    } else {  // ragged N (cosine scoring): guarded scalar stores
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col + j < gp.N) dstf[j] = x[j];
+                    }
+                } else {
+                    uint32_t h[16], l[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        __nv_bfloat16 h0, l0, h1, l1;
+                        split_bf16(x[2 * j], h0, l0);
+                        split_bf16(x[2 * j + 1], h1, l1);
+                        h[j] = pack_bf16x2(h0, h1);
+                        l[j] = pack_bf16x2(l0, l1);
+                    }
+                    __nv_bfloat16* obase = static_cast<__nv_bfloat16*>(ep.out) + ep.out_col0 + col;
+                    auto store_row = [&](int64_t r) {
+                        uint4* ph = reinterpret_cast<uint4*>(obase + r * ep.out_ld);
+                        uint4* pl = reinterpret_cast<uint4*>(obase + ep.out_plane_stride + r * ep.out_ld);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            ph[j] = make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+                            pl[j] = make_uint4(l[4 * j], l[4 * j + 1], l[4 * j + 2], l[4 * j + 3]);
+                        }
+                    };
+                    store_row(row);
+                    if (mirror_a >= 0) store_row(mirror_a);
+                    if (mirror_b >= 0) store_row(mirror_b);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty_bar(acc));
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// 3-D map over split planes [2][rows][ld] bf16, box = {64 cols, box_rows, 1 plane}, SWIZZLE_128B.
+static int encode_planes_map(CUtensorMap* m, const Planes& t, int box_rows) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return fail(PPV_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+    if ((reinterpret_cast<uintptr_t>(t.base) & 15) || (t.ld % 8) || (t.plane_stride % 8))
+        return fail(PPV_EINVAL, "planes tensor not 16-byte aligned");
+    cuuint64_t dims[3] = {cuuint64_t(t.ld), cuuint64_t(t.rows), 2};
+    cuuint64_t strides[2] = {cuuint64_t(t.ld) * 2, cuuint64_t(t.plane_stride) * 2};
+    cuuint32_t box[3] = {cuuint32_t(GEMM_BK), cuuint32_t(box_rows), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, t.base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(PPV_ECUDA, "cuTensorMapEncodeTiled failed, CUresult " + std::to_string(int(r)));
+    return PPV_OK;
+}
+
+int gemm_build(GemmParams* gp, const GemmSource* srcs, int nsrc, const Planes& W, int M, int N, const Epilogue& epi,
+               int BN) {
+    PPV_REQUIRE(BN == 64 || BN == 128 || BN == 256, "gemm_build: BN must be 64/128/256");
+    PPV_REQUIRE(epi.out_mode == OUT_F32 || N % 32 == 0, "gemm_build: planes output needs N % 32 == 0");
+    PPV_REQUIRE(!epi.rowgrp_bias || N % 32 == 0, "gemm_build: row-group bias needs N % 32 == 0");
+    memset(gp, 0, sizeof(*gp));
+    // distinct A tensors -> maps
+    const __nv_bfloat16* bases[GEMM_MAX_MAPS];
+    int nmaps = 0;
+    int ks = 0;
+    for (int i = 0; i < nsrc; ++i) {
+        const GemmSource& s = srcs[i];
+        PPV_REQUIRE(s.ncols % GEMM_BK == 0 && s.col0 % 8 == 0, "gemm_build: source K slice must be a multiple of 64");
+        PPV_REQUIRE(s.col0 + s.ncols <= s.t.ld, "gemm_build: source K slice exceeds the row");
+        int mi = -1;
+        for (int j = 0; j < nmaps; ++j)
+            if (bases[j] == s.t.base) mi = j;
+        if (mi < 0) {
+            PPV_REQUIRE(nmaps < GEMM_MAX_MAPS, "gemm_build: too many distinct A tensors");
+            mi = nmaps++;
+            bases[mi] = s.t.base;
+            int rc = encode_planes_map(&gp->mapA[mi], s.t, GEMM_BM);
+            if (rc) return rc;
+        }
+        for (int c = 0; c < s.ncols; c += GEMM_BK) {
+            PPV_REQUIRE(ks < GEMM_MAX_KSTEPS, "gemm_build: too many k-steps");
+            gp->ksteps[ks].map = int16_t(mi);
+            gp->ksteps[ks].row_off = int16_t(s.row_off);
+            gp->ksteps[ks].a_col = s.col0 + c;
+            ++ks;
+        }
+    }
+    for (int j = nmaps; j < GEMM_MAX_MAPS; ++j) gp->mapA[j] = gp->mapA[0];
+    PPV_REQUIRE(ks > 0, "gemm_build: empty K");
+    PPV_REQUIRE(W.ld == ks * GEMM_BK, "gemm_build: weight K does not match the k-steps");
+    PPV_REQUIRE(W.rows >= N, "gemm_build: weight rows < N");
+    int rc = encode_planes_map(&gp->mapB, W, BN);
+    if (rc) return rc;
+    gp->num_ksteps = ks;
+    gp->M = M;
+    gp->N = N;
+    gp->m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+    gp->n_tiles = (N + BN - 1) / BN;
+    gp->epi = epi;
+    if (epi.out_mode == OUT_PLANES) {
+        PPV_REQUIRE((epi.out_ld % 8) == 0 && (epi.out_col0 % 8) == 0 && (epi.out_plane_stride % 8) == 0,
+                    "gemm_build: planes output must be 16-byte aligned");
+    } else {
+        gp->epi.f32_vec_ok = ((epi.out_ld % 4) == 0 && (epi.out_col0 % 4) == 0 && (reinterpret_cast<uintptr_t>(epi.out) & 15) == 0) ? 1 : 0;
+    }
+    return PPV_OK;
+}
+
+template <int BN, int NSPLIT>
+static int launch_one(const GemmParams& gp, int num_sms, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN, NSPLIT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        PPV_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int tiles = gp.m_tiles * gp.n_tiles;
+    const int grid = std::min(tiles, num_sms);
+    gemm_tcgen05_kernel<BN, NSPLIT><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(gp);
+    PPV_LAUNCH_OK("gemm_tcgen05_kernel");
+    return PPV_OK;
+}
+
+int gemm_launch(const GemmParams& gp, int BN, int precision, int num_sms, cudaStream_t stream) {
+    const bool x3 = (precision == PPV_PREC_BF16X3);
+    switch (BN) {
+        case 64: return x3 ? launch_one<64, 3>(gp, num_sms, stream) : launch_one<64, 1>(gp, num_sms, stream);
+        case 128: return x3 ? launch_one<128, 3>(gp, num_sms, stream) : launch_one<128, 1>(gp, num_sms, stream);
+        case 256: return x3 ? launch_one<256, 3>(gp, num_sms, stream) : launch_one<256, 1>(gp, num_sms, stream);
+    }
+    return fail(PPV_EINVAL, "gemm_launch: bad BN");
+}
+
+}  // namespace ppv
