@@ -1,0 +1,118 @@
+"""ctypes binding of libppv_b200.so (C ABI: include/ppv_b200.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``csrc/Makefile`` and lives next to this package
+(``../lib/libppv_b200.so``).  Loading fails loudly: the product path has no CPU or eager-PyTorch fallback.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "lib", "libppv_b200.so"))
+
+PPV_PREC_BF16X3 = 0
+PPV_PREC_BF16 = 1
+PPV_MODEL_ECAPA_TDNN = 1
+
+
+class PPVError(RuntimeError):
+    pass
+
+
+class FbankCfg(C.Structure):
+    _fields_ = [("sample_rate", C.c_int), ("n_mels", C.c_int), ("frame_length_ms", C.c_float),
+                ("frame_shift_ms", C.c_float), ("preemph", C.c_float), ("low_freq", C.c_float),
+                ("high_freq", C.c_float), ("log_floor", C.c_float)]
+
+
+class EcapaCfg(C.Structure):
+    _fields_ = [("input_size", C.c_int), ("embd_dim", C.c_int), ("channels", C.c_int * 5),
+                ("kernel_sizes", C.c_int * 5), ("dilations", C.c_int * 5), ("attention_channels", C.c_int),
+                ("res2net_scale", C.c_int), ("se_channels", C.c_int), ("precision", C.c_int)]
+
+
+_P = C.c_void_p
+# name -> (restype, argtypes); this table is also what tests/test_abi.py checks against include/ppv_b200.h
+SIGNATURES = {
+    "ppv_version": (C.c_int, []),
+    "ppv_last_error": (C.c_int, [C.c_char_p, C.c_size_t]),
+    "ppv_device_sm_count": (C.c_int, []),
+    "ppv_fbank_default_cfg": (None, [C.POINTER(FbankCfg)]),
+    "ppv_fbank_create": (C.c_int, [C.POINTER(FbankCfg), C.POINTER(_P)]),
+    "ppv_fbank_destroy": (C.c_int, [_P]),
+    "ppv_fbank_num_frames": (C.c_int, [_P, C.c_int]),
+    "ppv_fbank_feature_dim": (C.c_int, [_P]),
+    "ppv_fbank_forward": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P]),
+    "ppv_ecapa_default_cfg": (None, [C.POINTER(EcapaCfg)]),
+    "ppv_model_create": (C.c_int, [C.c_int, _P, C.POINTER(_P)]),
+    "ppv_model_destroy": (C.c_int, [_P]),
+    "ppv_model_load_weight": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int]),
+    "ppv_model_finalize": (C.c_int, [_P]),
+    "ppv_model_set_precision": (C.c_int, [_P, C.c_int]),
+    "ppv_model_embd_dim": (C.c_int, [_P]),
+    "ppv_model_workspace_bytes": (C.c_size_t, [_P, C.c_int, C.c_int]),
+    "ppv_model_forward": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, C.c_size_t, _P]),
+    "ppv_model_forward_wav": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P, _P, C.c_size_t, _P]),
+    "ppv_model_read_tap": (C.c_int, [_P, C.c_char_p, _P, C.c_size_t, _P]),
+    "ppv_cosine_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "ppv_cosine_matrix": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_size_t, _P]),
+    "ppv_cosine_pairlist": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, _P, _P]),
+    "ppv_aam_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "ppv_aam_forward": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float,
+                                  _P, _P, _P, C.c_size_t, _P]),
+    "ppv_aam_backward": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,
+                                   C.c_float, _P, _P, _P, C.c_size_t, _P]),
+    "ppv_gemm_test_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "ppv_gemm_test": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P,
+                                C.c_size_t, _P]),
+}
+
+_lib = None
+
+
+def load(path: str = None):
+    """dlopen the library and declare every prototype.  No compute, no GPU needed for this step."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise PPVError(f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       f"(there is no CPU fallback for the ppvector hot path)")
+    lib = C.CDLL(p)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def last_error(lib=None) -> str:
+    lib = lib or load()
+    buf = C.create_string_buffer(2048)
+    lib.ppv_last_error(buf, 2048)
+    return buf.value.decode("utf-8", "replace")
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        raise PPVError(f"{what} failed with status {rc}: {last_error()}")
+
+
+def ptr(t):
+    """Device pointer of a contiguous torch tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "ppv: tensor must be contiguous"
+    return C.c_void_p(t.data_ptr())
+
+
+def require_cuda(t, name="tensor"):
+    if not t.is_cuda:
+        raise PPVError(f"ppv: {name} must be a CUDA tensor -- the ppvector hot path has no CPU fallback")
+
+
+def current_stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,239 @@
+"""EcapaTdnn -- drop-in for ppvector/models/ecapa_tdnn.py:145-276 of the reference.
+
+The module tree and parameter names equal the reference's Paddle ``state_dict`` (``blocks.0.conv.conv.weight``,
+``blocks.1.res2net_block.blocks.3.norm.norm._variance`` ...), so reference checkpoints map 1:1.  The modules
+hold parameters only; ``forward`` is ONE call into libppv_b200 (``ppv_model_forward``): tcgen05/TMA gather-GEMMs
+with fused bias/ReLU/BatchNorm epilogues plus the SE / ASP reductions (csrc/ecapa.cu).  Eval mode only
+(training kernels are SURVEY.md §8 row a11, not built yet); there is no torch fallback.
+"""
+import ctypes as C
+import math
+
+import torch
+from torch import nn
+
+from ppvector import _lib
+
+__all__ = ['EcapaTdnn']
+
+
+class _ConvParams(nn.Module):
+    """Parameter holder named like paddle.nn.Conv1D (weight [Cout,Cin,k], bias [Cout])."""
+
+    def __init__(self, cin, cout, k):
+        super().__init__()
+        bound = 1.0 / math.sqrt(cin * k)
+        self.weight = nn.Parameter(torch.empty(cout, cin, k).uniform_(-bound, bound))
+        self.bias = nn.Parameter(torch.zeros(cout))
+
+
+class Conv1d(nn.Module):
+    """reference: ppvector/models/utils.py:22-93 (wrapper whose inner layer is ``.conv``)"""
+
+    def __init__(self, in_channels, out_channels, kernel_size, dilation=1):
+        super().__init__()
+        self.kernel_size, self.dilation = kernel_size, dilation
+        self.conv = _ConvParams(in_channels, out_channels, kernel_size)
+
+
+class _BNParams(nn.Module):
+    """Parameter holder named like paddle.nn.BatchNorm1D (weight, bias, _mean, _variance)."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(c))
+        self.bias = nn.Parameter(torch.zeros(c))
+        self.register_buffer('_mean', torch.zeros(c))
+        self.register_buffer('_variance', torch.ones(c))
+
+
+class BatchNorm1d(nn.Module):
+    """reference: ppvector/models/utils.py:96-119 (wrapper whose inner layer is ``.norm``)"""
+
+    def __init__(self, input_size):
+        super().__init__()
+        self.norm = _BNParams(input_size)
+
+
+class TDNNBlock(nn.Module):
+    """reference: ppvector/models/utils.py:122-148"""
+
+    def __init__(self, in_channels, out_channels, kernel_size, dilation):
+        super().__init__()
+        self.conv = Conv1d(in_channels, out_channels, kernel_size, dilation)
+        self.norm = BatchNorm1d(out_channels)
+
+
+class Res2NetBlock(nn.Module):
+    """reference: ecapa_tdnn.py:11-34"""
+
+    def __init__(self, in_channels, out_channels, scale=8, dilation=1):
+        super().__init__()
+        assert in_channels % scale == 0 and out_channels % scale == 0
+        self.blocks = nn.ModuleList([TDNNBlock(in_channels // scale, out_channels // scale, 3, dilation)
+                                     for _ in range(scale - 1)])
+        self.scale = scale
+
+
+class SEBlock(nn.Module):
+    """reference: ecapa_tdnn.py:50-67"""
+
+    def __init__(self, in_channels, se_channels, out_channels):
+        super().__init__()
+        self.conv1 = Conv1d(in_channels, se_channels, 1)
+        self.conv2 = Conv1d(se_channels, out_channels, 1)
+
+
+class SERes2NetBlock(nn.Module):
+    """reference: ecapa_tdnn.py:85-130"""
+
+    def __init__(self, in_channels, out_channels, res2net_scale=8, se_channels=128, kernel_size=1, dilation=1):
+        super().__init__()
+        self.tdnn1 = TDNNBlock(in_channels, out_channels, 1, 1)
+        self.res2net_block = Res2NetBlock(out_channels, out_channels, res2net_scale, dilation)
+        self.tdnn2 = TDNNBlock(out_channels, out_channels, 1, 1)
+        self.se_block = SEBlock(out_channels, se_channels, out_channels)
+        if in_channels != out_channels:
+            raise NotImplementedError('SERes2NetBlock shortcut conv (in != out channels) is not implemented on B200')
+
+
+class AttentiveStatisticsPooling(nn.Module):
+    """reference: ppvector/models/pooling.py:69-84"""
+
+    def __init__(self, channels, attention_channels=128, global_context=True):
+        super().__init__()
+        if not global_context:
+            raise NotImplementedError('ASP without global_context is not implemented on B200')
+        self.tdnn = TDNNBlock(channels * 3, attention_channels, 1, 1)
+        self.conv = Conv1d(attention_channels, channels, 1)
+
+
+class EcapaTdnn(nn.Module):
+    def __init__(self, input_size, embd_dim=192, pooling_type="ASP", activation=None,
+                 channels=[512, 512, 512, 512, 1536], kernel_sizes=[5, 3, 3, 3, 1], dilations=[1, 2, 3, 4, 1],
+                 attention_channels=128, res2net_scale=8, se_channels=128, global_context=True,
+                 precision='bf16x3'):
+        super().__init__()
+        assert len(channels) == len(kernel_sizes) == len(dilations) == 5
+        if pooling_type != "ASP":
+            raise NotImplementedError(f'pooling_type {pooling_type} is not implemented on B200 (ASP only)')
+        self.input_size, self.channels, self.embd_dim = input_size, list(channels), embd_dim
+        self.kernel_sizes, self.dilations = list(kernel_sizes), list(dilations)
+        self.attention_channels, self.res2net_scale, self.se_channels = attention_channels, res2net_scale, se_channels
+        self.blocks = nn.ModuleList()
+        self.blocks.append(TDNNBlock(input_size, channels[0], kernel_sizes[0], dilations[0]))
+        for i in range(1, len(channels) - 1):
+            self.blocks.append(SERes2NetBlock(channels[i - 1], channels[i], res2net_scale, se_channels,
+                                              kernel_sizes[i], dilations[i]))
+        self.mfa = TDNNBlock(channels[-1], channels[-1], kernel_sizes[-1], dilations[-1])
+        self.asp = AttentiveStatisticsPooling(channels[-1], attention_channels, global_context)
+        self.asp_bn = BatchNorm1d(channels[-1] * 2)
+        self.fc = Conv1d(channels[-1] * 2, embd_dim, 1)
+        self.precision = precision
+        self._handle = None
+        self._ws = None
+
+    # ---- C-ABI plumbing -------------------------------------------------------------------------------------
+    def _prec_code(self):
+        return {'bf16x3': _lib.PPV_PREC_BF16X3, 'bf16': _lib.PPV_PREC_BF16}[self.precision]
+
+    def invalidate(self):
+        """Drop the device-side copy of the weights (call after changing parameters / load_state_dict)."""
+        if self._handle is not None:
+            _lib.load().ppv_model_destroy(self._handle)
+            self._handle = None
+
+    def load_state_dict(self, *a, **k):
+        r = super().load_state_dict(*a, **k)
+        self.invalidate()
+        return r
+
+    def _get_handle(self):
+        if self._handle is not None:
+            return self._handle
+        lib = _lib.load()
+        cfg = _lib.EcapaCfg()
+        lib.ppv_ecapa_default_cfg(C.byref(cfg))
+        cfg.input_size, cfg.embd_dim = self.input_size, self.embd_dim
+        for i in range(5):
+            cfg.channels[i], cfg.kernel_sizes[i], cfg.dilations[i] = self.channels[i], self.kernel_sizes[i], self.dilations[i]
+        cfg.attention_channels, cfg.res2net_scale, cfg.se_channels = self.attention_channels, self.res2net_scale, self.se_channels
+        cfg.precision = self._prec_code()
+        h = C.c_void_p()
+        _lib.check(lib.ppv_model_create(_lib.PPV_MODEL_ECAPA_TDNN, C.byref(cfg), C.byref(h)), 'ppv_model_create')
+        for name, t in self.state_dict().items():
+            t = t.detach().to(torch.float32).contiguous()
+            shape = (C.c_int64 * t.dim())(*t.shape)
+            _lib.check(lib.ppv_model_load_weight(h, name.encode(), C.c_void_p(t.data_ptr()), shape, t.dim()),
+                       f'ppv_model_load_weight({name})')
+        _lib.check(lib.ppv_model_finalize(h), 'ppv_model_finalize')
+        self._handle = h
+        return h
+
+    def set_precision(self, precision: str):
+        self.precision = precision
+        if self._handle is not None:
+            _lib.check(_lib.load().ppv_model_set_precision(self._handle, self._prec_code()), 'ppv_model_set_precision')
+
+    def _workspace(self, B, T, device):
+        need = _lib.load().ppv_model_workspace_bytes(self._get_handle(), B, T)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=device)
+        return self._ws
+
+    def __del__(self):
+        try:
+            self.invalidate()
+        except Exception:
+            pass
+
+    # ---- the reference surface ------------------------------------------------------------------------------
+    def forward(self, x, lengths=None):
+        """reference: ecapa_tdnn.py:245-276.  x [N, time, freq] float32 CUDA -> [N, embd_dim]."""
+        if lengths is not None:
+            raise NotImplementedError('lengths masking is never used by the reference callers and is not implemented')
+        if self.training:
+            raise _lib.PPVError('EcapaTdnn on B200 implements the eval-mode forward only; call .eval()')
+        _lib.require_cuda(x, 'x')
+        x = x.to(torch.float32).contiguous()
+        B, T, F = x.shape
+        assert F == self.input_size
+        with torch.cuda.device(x.device):
+            h = self._get_handle()
+            ws = self._workspace(B, T, x.device)
+            emb = torch.empty((B, self.embd_dim), dtype=torch.float32, device=x.device)
+            _lib.check(_lib.load().ppv_model_forward(h, _lib.ptr(x), B, T, _lib.ptr(emb), C.c_void_p(ws.data_ptr()),
+                                                      ws.numel(), _lib.current_stream()), 'ppv_model_forward')
+        return emb
+
+    def forward_wav(self, featurizer, waveforms, input_lens_ratio=None):
+        """Fused waveform -> embedding path (``ppv_model_forward_wav``): equals
+        ``self(featurizer(waveforms, input_lens_ratio))`` without materialising the [B,T,F] features."""
+        _lib.require_cuda(waveforms, 'waveforms')
+        if waveforms.dim() == 1:
+            waveforms = waveforms.unsqueeze(0)
+        wav = waveforms.to(torch.float32).contiguous()
+        B, L = wav.shape
+        T = featurizer.num_frames(L)
+        ratio = None
+        if input_lens_ratio is not None:
+            ratio = torch.as_tensor(input_lens_ratio, dtype=torch.float32, device=wav.device).contiguous()
+        with torch.cuda.device(wav.device):
+            h = self._get_handle()
+            ws = self._workspace(B, T, wav.device)
+            emb = torch.empty((B, self.embd_dim), dtype=torch.float32, device=wav.device)
+            _lib.check(_lib.load().ppv_model_forward_wav(h, featurizer._get_handle(), _lib.ptr(wav), _lib.ptr(ratio), B, L,
+                                                          _lib.ptr(emb), C.c_void_p(ws.data_ptr()), ws.numel(),
+                                                          _lib.current_stream()), 'ppv_model_forward_wav')
+        return emb
+
+    def read_tap(self, name, B, T):
+        """Debug / parity: an internal activation of the last forward as fp32 ([B,T,C], or [B,2C] for 'asp')."""
+        C3 = self.channels[-1]
+        cols = {'feat': self.input_size, 'blocks.0': self.channels[0], 'blocks.1': self.channels[1],
+                'blocks.2': self.channels[2], 'blocks.3': self.channels[3], 'mfa': C3}
+        dev = self._ws.device
+        out = torch.empty((B, 2 * C3) if name == 'asp' else (B, T, cols[name]), dtype=torch.float32, device=dev)
+        _lib.check(_lib.load().ppv_model_read_tap(self._get_handle(), name.encode(), _lib.ptr(out), out.numel(),
+                                                   _lib.current_stream()), 'ppv_model_read_tap')
+        return out
