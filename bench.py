@@ -1,0 +1,278 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json metric: utterances/sec, ECAPA-TDNN + Fbank-80, 3 s @ 16 kHz, waveform -> 192-d
+embedding (configs[1]: batch 256 x 3 s synthetic audio per GPU).
+
+  python bench.py [--gpus N --steps K --warmup W] [--impl ours|reference] [--precision bf16x3|bf16]
+
+One "step" = one batch of 256 utterances through the whole hot path.
+  value     device-resident waveforms -> embeddings on device, CUDA events around the K timed steps
+  e2e       the same through PPVectorPredictor.extract_embeddings_pinned: pinned host fp32 waveforms -> H2D ->
+            hot path -> D2H embeddings, every step
+  roofline  tensor-core gather-GEMM (the dominant kernel): algorithmic FLOPs / its summed launch time,
+            measured with CUDA events on the launching stream inside the timed region
+  cpu_baseline  the oracle (torch CPU port of the reference path; Paddle is not installable) on a bounded sample
+N > 1: one process per GPU (torchrun), each rank extracts its own 256-utterance batches (weak scaling, no
+data-path collective); barrier + synchronize on both sides; elapsed = max over ranks.
+--impl reference: the reference's own CPU path is pure Python over paddle/paddleaudio, which cannot be installed
+here (no network); the timed stand-in is the oracle port on all host cores (kind = "port").
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "voiceprintrecognition-paddlepaddle_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+BATCH = 256
+SAMPLES = 48000
+FRAMES = 298
+METRIC = "utterances/sec ECAPA-TDNN Fbank80 3s embed extract"
+
+
+def algorithmic_flops_per_utt(T=FRAMES, F=80, C=512, scale=8, A=128, S=128, E=192, k0=5):
+    """2 x MACs of the reference graph with ASP's tiled [mean;std] folded into a bias
+    (what this build executes): 2.857 GFLOP per 3 s utterance."""
+    w = C // scale
+    C3 = 3 * C
+    per_frame = k0 * F * C + 3 * (C * C + (scale - 1) * 3 * w * w + C * C) + C3 * C3 + C3 * A + A * C3
+    per_utt = 3 * (2 * C * S) + 2 * C3 * A + 2 * C3 * E
+    return 2.0 * (per_frame * T + per_utt)
+
+
+def synth_wave(batch, seed):
+    g = torch.Generator().manual_seed(seed)
+    return (0.1 * torch.randn(batch, SAMPLES, generator=g)).clamp_(-1, 1)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_throughput(n_utts, threads):
+    """Oracle port of the reference CPU path (AudioFeaturizer('Fbank') + EcapaTdnn, fp32, eval) on host cores."""
+    from oracle import ecapa as oe
+    from oracle import fbank as ofb
+    torch.set_num_threads(threads)
+    W = oe.make_ecapa_weights(seed=1000, dtype=torch.float32)
+    wav = synth_wave(n_utts, 1000).numpy()
+    best = None
+    with torch.no_grad():
+        for _ in range(2):
+            t0 = time.perf_counter()
+            feat = torch.from_numpy(ofb.audio_featurizer_fbank(wav, None, n_mels=80))  # per-utterance loop, like featurizer.py:94
+            for i in range(0, n_utts, 32):  # predict.py:265: chunks of 32
+                oe.ecapa_forward(feat[i:i + 32], W)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return n_utts / best
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n = 32
+    vals = []
+    for _ in range(max(1, min(args.steps, 3))):
+        vals.append(cpu_oracle_throughput(n, cores))
+    v = max(vals)
+    line = {"metric": METRIC, "value": v, "unit": "utterances/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * BATCH / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": "ECAPA-TDNN (configs/ecapa_tdnn.yml) Fbank-80 embedding extraction, 3 s @ 16 kHz synthetic audio",
+                       "batch_per_gpu": BATCH, "parallelism": "host cores"},
+            "cpu_baseline": {"value": v, "unit": "utterances/s", "cores": cores, "kind": "port",
+                             "sample": f"{n} utterances x 3 s per step, best of 2, oracle port (torch CPU fp32); PaddlePaddle is not installable offline"},
+            "e2e": {"value": v, "unit": "utterances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import ctypes as C
+    from oracle import ecapa as oe  # weights only (seeded init shared with the CPU baseline)
+    from ppvector import _lib
+    from ppvector.predict import PPVectorPredictor
+
+    assert torch.cuda.is_available(), "bench.py --impl ours needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    import yaml
+    cfg = yaml.load(open(os.path.join(ROOT, "configs", "ecapa_tdnn.yml")), Loader=yaml.FullLoader)
+    Wts = {k: v.numpy() for k, v in oe.make_ecapa_weights(seed=1000, dtype=torch.float32).items()}
+    pred = PPVectorPredictor(cfg, model_path=None, use_gpu=True, state_dict=Wts)
+    pred.predictor.set_precision(args.precision)
+    model, fz = pred.predictor, pred._audio_featurizer
+    lib = _lib.load()
+
+    # two distinct device-resident batches; working set per step (49 MB waveforms + ~2.2 GB activations) >> 126 MB L2
+    wavs = [synth_wave(BATCH, 1000 + rank * 10 + i).to(dev) for i in range(2)]
+    host = [synth_wave(BATCH, 2000 + rank * 10 + i).pin_memory() for i in range(2)]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ------------------------------------------------------------------------------
+    for i in range(args.warmup):
+        emb = model.forward_wav(fz, wavs[i % 2])
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    _lib.check(lib.ppv_model_profile(model._get_handle(), 1), "ppv_model_profile")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        emb = model.forward_wav(fz, wavs[i % 2])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    g_ms, o_ms, g_n, o_n = C.c_double(), C.c_double(), C.c_int64(), C.c_int64()
+    _lib.check(lib.ppv_model_profile_read(model._get_handle(), C.byref(g_ms), C.byref(o_ms), C.byref(g_n), C.byref(o_n)),
+               "ppv_model_profile_read")
+    _lib.check(lib.ppv_model_profile(model._get_handle(), 0), "ppv_model_profile")
+    clk = clocks.stop() if rank == 0 else None
+    assert torch.isfinite(emb).all()
+
+    # ---- end to end through the public API (host buffers) -----------------------------------------------------
+    for i in range(3):
+        pred.extract_embeddings_pinned(host[i % 2])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        out = pred.extract_embeddings_pinned(host[i % 2])
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    assert np.isfinite(out.numpy()).all()
+
+    times = torch.tensor([ms / 1000.0, e2e_s], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_s, e2e_s = times.tolist()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16, kernel timed inside a long step)" if peaks else \
+            "fallback 1.4 PF sustained (B200_PROFILING.md)"
+        flops_step = algorithmic_flops_per_utt() * BATCH
+        gemm_s_per_step = g_ms.value / 1000.0 / args.steps
+        achieved = flops_step / gemm_s_per_step / 1e12
+        value = world * BATCH * args.steps / dev_s
+        line = {
+            "metric": METRIC, "value": value, "unit": "utterances/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate; fp32-grade)" if args.precision == "bf16x3" else "bf16",
+            "data": "synthetic",
+            "config": {"workload": "ECAPA-TDNN (configs/ecapa_tdnn.yml) Fbank-80 embedding extraction, batch 256 x 3 s @ 16 kHz synthetic audio per GPU (BASELINE configs[1])",
+                       "batch_per_gpu": BATCH, "global_batch": BATCH * world, "samples": SAMPLES, "frames": FRAMES,
+                       "parallelism": f"dp{world} (independent utterance shards, no collective)",
+                       "l2": "two alternating input batches; per-step working set ~2.2 GB >> 126 MB L2"},
+            "e2e": {"value": world * BATCH * args.steps / e2e_s, "unit": "utterances/s",
+                    "h2d_bytes_per_step": BATCH * SAMPLES * 4, "d2h_bytes_per_step": BATCH * 192 * 4,
+                    "api": "PPVectorPredictor.extract_embeddings_pinned (pinned fp32 waveforms -> embeddings on host)"},
+            "gpu_launches": int(g_n.value + o_n.value),
+            "clocks": clk,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                         "traffic": None, "kernel": "gemm_tcgen05_kernel (all conv / linear layers)",
+                         "launches_per_step": g_n.value / args.steps, "ms_per_step_in_kernel": 1000.0 * gemm_s_per_step,
+                         "other_kernels_ms_per_step": o_ms.value / args.steps,
+                         "algorithmic_gflop_per_utt": algorithmic_flops_per_utt() / 1e9,
+                         "executed_mma_multiple": 3 if args.precision == "bf16x3" else 1, "peak_source": peak_src},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            cores = os.cpu_count() or 1
+            n = 32
+            v = cpu_oracle_throughput(n, cores)
+            line["cpu_baseline"] = {"value": v, "unit": "utterances/s", "cores": cores, "kind": "port",
+                                    "sample": f"{n} utterances x 3 s, best of 2, oracle port of AudioFeaturizer+EcapaTdnn (torch CPU fp32)"}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

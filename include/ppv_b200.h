@@ -110,6 +110,13 @@ int ppv_model_forward_wav(ppv_model_t* h, ppv_fbank_t* fb, const float* wav, con
  * name in {"feat","blocks.0","blocks.1","blocks.2","blocks.3","mfa","asp"}; out is [B,T,C] ([B,C] for asp). */
 int ppv_model_read_tap(ppv_model_t* h, const char* name, float* out, size_t out_elems, void* stream);
 
+/* Measurement hooks (bench.py): CUDA events around every kernel group of the forward, on the launching stream.
+ * profile(h,1) starts recording; profile_read sums the durations since then (tensor-core GEMM launches vs the
+ * HBM-bound kernels), reports how many kernels were launched, synchronises on the last event and resets. */
+int ppv_model_profile(ppv_model_t* h, int enable);
+int ppv_model_profile_read(ppv_model_t* h, double* gemm_ms, double* other_ms, int64_t* gemm_launches,
+                           int64_t* other_launches);
+
 /* ---------------------------------------------------------------------------------------------
  * Cosine scoring.  Replaces ppvector/predict.py:279-283 (contrast), :173-187 (retrieval:
  * sklearn cosine_similarity) and ppvector/trainer.py:416-423 (eval trial x enrol matrix).

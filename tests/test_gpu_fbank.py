@@ -60,7 +60,8 @@ def test_ragged_lengths(cuda, fz, L):
 
 def test_silence_hits_log_floor_and_short_input_errors(cuda, fz):
     out = fz(torch.zeros(2, 1600, device=cuda))
-    assert torch.all(out == 0)  # log(eps) everywhere, minus its own mean
+    # log(eps) everywhere, minus its own mean: exactly 0 up to the fp32 rounding of an 8-term sum (1 ulp of 15.94)
+    assert out.abs().max().item() < 2e-6
     from ppvector._lib import PPVError
     with pytest.raises(PPVError):
         fz(torch.zeros(1, 399, device=cuda))

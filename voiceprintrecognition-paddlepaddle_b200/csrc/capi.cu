@@ -190,6 +190,17 @@ int ppv_model_read_tap(ppv_model_t* h, const char* name, float* out, size_t out_
     PPV_GUARD_END
 }
 
+int ppv_model_profile(ppv_model_t* h, int enable) {
+    PPV_REQUIRE(h, "ppv_model_profile: null model");
+    return ecapa_profile(h->ecapa, enable);
+}
+int ppv_model_profile_read(ppv_model_t* h, double* gemm_ms, double* other_ms, int64_t* gemm_launches, int64_t* other_launches) {
+    PPV_GUARD_BEGIN
+    PPV_REQUIRE(h, "ppv_model_profile_read: null model");
+    return ecapa_profile_read(h->ecapa, gemm_ms, other_ms, gemm_launches, other_launches);
+    PPV_GUARD_END
+}
+
 // ---------------------------------------------------------------- cosine scoring
 size_t ppv_cosine_workspace_bytes(int M, int N, int D) { return cosine_workspace_bytes(M, N, D); }
 int ppv_cosine_matrix(const float* A, const float* Bm, int M, int N, int D, float* out, void* ws, size_t ws_bytes, void* stream) {

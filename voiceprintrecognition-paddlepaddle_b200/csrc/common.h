@@ -143,6 +143,8 @@ size_t ecapa_workspace_bytes(const EcapaModel* m, int B, int T);
 int ecapa_forward(EcapaModel* m, const float* feat, Fbank* fb, const float* wav, const float* lens_ratio, int B, int T, int L,
                   float* emb, void* ws, size_t ws_bytes, cudaStream_t st);
 int ecapa_read_tap(EcapaModel* m, const char* name, float* out, size_t out_elems, cudaStream_t st);
+int ecapa_profile(EcapaModel* m, int enable);
+int ecapa_profile_read(EcapaModel* m, double* gemm_ms, double* other_ms, int64_t* gemm_launches, int64_t* other_launches);
 
 // ---- cosine.cu / aam.cu -----------------------------------------------------------------------------
 size_t cosine_workspace_bytes(int M, int N, int D);

@@ -75,6 +75,12 @@ struct EcapaModel {
     float *se_mean = nullptr, *se_scale = nullptr, *fold_out = nullptr, *logits = nullptr, *pooled_raw = nullptr,
           *raw_logmel = nullptr, *emb_out = nullptr;
     int Tp = 0;
+    // profiling (bench.py roofline): CUDA events around every launch group of the forward
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev;   // pairs
+    std::vector<int> prof_kind;         // 0 = tensor-core GEMM, 1 = other kernels
+    size_t prof_used = 0;
+    int64_t launches_gemm = 0, launches_other = 0;
 };
 
 // ------------------------------------------------------------------------------------------------ create / load
@@ -113,6 +119,7 @@ int ecapa_create(const ppv_ecapa_cfg* cfg, EcapaModel** out) {
 
 void ecapa_destroy(EcapaModel* m) {
     if (!m) return;
+    for (cudaEvent_t e : m->prof_ev) cudaEventDestroy(e);
     cudaFree(m->arena);
     delete m;
 }
@@ -541,12 +548,37 @@ int ecapa_forward(EcapaModel* m, const float* feat, Fbank* fb, const float* wav,
     const int Tp = m->Tp, P = m->P, C = m->C, C3 = m->C3;
     const int64_t R = int64_t(B) * Tp;
     int rc;
-    if (wav)
+    auto prof_mark = [&](int kind, bool begin) {
+        if (!m->prof_on) return;
+        if (begin) {
+            if (m->prof_used + 2 > m->prof_ev.size()) {
+                cudaEvent_t a, b;
+                cudaEventCreate(&a);
+                cudaEventCreate(&b);
+                m->prof_ev.push_back(a);
+                m->prof_ev.push_back(b);
+                m->prof_kind.push_back(kind);
+            }
+            m->prof_kind[m->prof_used / 2] = kind;
+            cudaEventRecord(m->prof_ev[m->prof_used], st);
+        } else {
+            cudaEventRecord(m->prof_ev[m->prof_used + 1], st);
+            m->prof_used += 2;
+        }
+    };
+    prof_mark(1, true);
+    if (wav) {
         rc = fbank_run(fb, wav, lens_ratio, B, L, m->raw_logmel, nullptr, m->bufs[B_FEAT], P, Tp, st);
-    else
+        m->launches_other += 3;
+    } else {
         rc = launch_pack_features(feat, B, T, m->cfg.input_size, m->bufs[B_FEAT], P, Tp, st);
+        m->launches_other += 1;
+    }
+    prof_mark(1, false);
     if (rc) return rc;
     for (const Step& s : m->steps) {
+        prof_mark(s.kind == Step::GEMM ? 0 : 1, true);
+        if (s.kind == Step::GEMM) m->launches_gemm += 1; else m->launches_other += 1;
         switch (s.kind) {
             case Step::GEMM: rc = gemm_launch(s.gp, s.BN, m->precision, m->num_sms, st); break;
             case Step::SE_SQUEEZE:
@@ -570,9 +602,37 @@ int ecapa_forward(EcapaModel* m, const float* feat, Fbank* fb, const float* wav,
                                      m->bufs[B_POOL], m->pooled_raw, st);
                 break;
         }
+        prof_mark(0, false);
         if (rc) return rc;
     }
     PPV_CUDA_OK(cudaMemcpyAsync(emb, m->emb_out, size_t(B) * m->cfg.embd_dim * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return PPV_OK;
+}
+
+int ecapa_profile(EcapaModel* m, int enable) {
+    PPV_REQUIRE(m, "ecapa_profile: null model");
+    m->prof_on = enable != 0;
+    m->prof_used = 0;
+    m->launches_gemm = m->launches_other = 0;
+    return PPV_OK;
+}
+
+// Sums the event-pair durations recorded since ecapa_profile(m, 1); synchronises on the last event.
+int ecapa_profile_read(EcapaModel* m, double* gemm_ms, double* other_ms, int64_t* gemm_launches, int64_t* other_launches) {
+    PPV_REQUIRE(m && gemm_ms && other_ms && gemm_launches && other_launches, "ecapa_profile_read: null argument");
+    double g = 0, o = 0;
+    if (m->prof_used >= 2) PPV_CUDA_OK(cudaEventSynchronize(m->prof_ev[m->prof_used - 1]));
+    for (size_t i = 0; i + 1 < m->prof_used; i += 2) {
+        float ms = 0.f;
+        PPV_CUDA_OK(cudaEventElapsedTime(&ms, m->prof_ev[i], m->prof_ev[i + 1]));
+        (m->prof_kind[i / 2] == 0 ? g : o) += ms;
+    }
+    *gemm_ms = g;
+    *other_ms = o;
+    *gemm_launches = m->launches_gemm;
+    *other_launches = m->launches_other;
+    m->prof_used = 0;
+    m->launches_gemm = m->launches_other = 0;
     return PPV_OK;
 }
 

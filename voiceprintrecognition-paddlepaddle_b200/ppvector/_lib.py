@@ -53,6 +53,9 @@ SIGNATURES = {
     "ppv_model_forward": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, C.c_size_t, _P]),
     "ppv_model_forward_wav": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P, _P, C.c_size_t, _P]),
     "ppv_model_read_tap": (C.c_int, [_P, C.c_char_p, _P, C.c_size_t, _P]),
+    "ppv_model_profile": (C.c_int, [_P, C.c_int]),
+    "ppv_model_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64),
+                                         C.POINTER(C.c_int64)]),
     "ppv_cosine_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "ppv_cosine_matrix": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_size_t, _P]),
     "ppv_cosine_pairlist": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, _P, _P]),
