@@ -66,7 +66,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -103,6 +103,18 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def cpu_oracle_best(n_utts):
+    """Time the oracle port at several intra-op thread counts (more threads is not always faster for these small
+    convolutions) and keep the best: generous to the baseline.  Returns (utt/s, threads)."""
+    cores = os.cpu_count() or 1
+    best = (0.0, cores)
+    for th in sorted({cores, min(cores, 64), min(cores, 32), min(cores, 16), min(cores, 8)}, reverse=True):
+        v = cpu_oracle_throughput(n_utts, th)
+        if v > best[0]:
+            best = (v, th)
+    return best
+
+
 def cpu_oracle_throughput(n_utts, threads):
     """Oracle port of the reference CPU path (AudioFeaturizer('Fbank') + EcapaTdnn, fp32, eval) on host cores."""
     from oracle import ecapa as oe
@@ -125,12 +137,8 @@ def cpu_oracle_throughput(n_utts, threads):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
     n = 32
-    vals = []
-    for _ in range(max(1, min(args.steps, 3))):
-        vals.append(cpu_oracle_throughput(n, cores))
-    v = max(vals)
+    v, cores = cpu_oracle_best(n)
     line = {"metric": METRIC, "value": v, "unit": "utterances/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 * BATCH / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "reference",
@@ -146,8 +154,8 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -264,9 +272,8 @@ def main():
                          "executed_mma_multiple": 3 if args.precision == "bf16x3" else 1, "peak_source": peak_src},
         }
         if not args.no_cpu_baseline and world == 1:
-            cores = os.cpu_count() or 1
             n = 32
-            v = cpu_oracle_throughput(n, cores)
+            v, cores = cpu_oracle_best(n)
             line["cpu_baseline"] = {"value": v, "unit": "utterances/s", "cores": cores, "kind": "port",
                                     "sample": f"{n} utterances x 3 s, best of 2, oracle port of AudioFeaturizer+EcapaTdnn (torch CPU fp32)"}
         print(json.dumps(line), flush=True)

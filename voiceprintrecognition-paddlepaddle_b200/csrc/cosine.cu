@@ -115,9 +115,9 @@ __global__ void __launch_bounds__(256)
 }
 
 int cosine_pairlist(const float* E, const int32_t* idx, int64_t P, int n, int D, float* out, cudaStream_t st) {
-    PPV_REQUIRE(E && idx && out, "cosine_pairlist: null argument");
-    PPV_REQUIRE(P >= 0 && n > 0 && D > 0, "cosine_pairlist: bad sizes");
     if (P == 0) return PPV_OK;
+    PPV_REQUIRE(E && idx && out, "cosine_pairlist: null argument");
+    PPV_REQUIRE(P > 0 && n > 0 && D > 0, "cosine_pairlist: bad sizes");
     const int64_t threads = P * 8;
     cosine_pairlist_kernel<<<unsigned((threads + 255) / 256), 256, 0, st>>>(E, idx, P, n, D, out);
     PPV_LAUNCH_OK("cosine_pairlist_kernel");

@@ -44,6 +44,8 @@ def cosine_pairlist(E, idx):
     P = idx.shape[0]
     n, D = E.shape
     out = torch.empty((P,), dtype=torch.float32, device=E.device)
+    if P == 0:
+        return out
     with torch.cuda.device(E.device):
         _lib.check(_lib.load().ppv_cosine_pairlist(_lib.ptr(E), _lib.ptr(idx), P, n, D, _lib.ptr(out), _lib.current_stream()),
                    'ppv_cosine_pairlist')
