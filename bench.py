@@ -6,8 +6,8 @@ embedding (configs[1]: batch 256 x 3 s synthetic audio per GPU).
 
 One "step" = one batch of 256 utterances through the whole hot path.
   value     device-resident waveforms -> embeddings on device, CUDA events around the K timed steps
-  e2e       the same through PPVectorPredictor.extract_embeddings_pinned: pinned host fp32 waveforms -> H2D ->
-            hot path -> D2H embeddings, every step
+  e2e       the same through PPVectorPredictor.extract_embeddings_stream: pinned host fp32 waveforms -> H2D (copy
+            stream, overlapped with the previous batch's kernels) -> hot path -> D2H embeddings, every step
   roofline  tensor-core gather-GEMM (the dominant kernel): algorithmic FLOPs / its summed launch time,
             measured with CUDA events on the launching stream inside the timed region
   cpu_baseline  the oracle (torch CPU port of the reference path; Paddle is not installable) on a bounded sample
@@ -221,12 +221,12 @@ def main():
     assert torch.isfinite(emb).all()
 
     # ---- end to end through the public API (host buffers) -----------------------------------------------------
-    for i in range(3):
-        pred.extract_embeddings_pinned(host[i % 2])
+    for out in pred.extract_embeddings_stream(host[i % 2] for i in range(3)):
+        pass
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        out = pred.extract_embeddings_pinned(host[i % 2])
+    for out in pred.extract_embeddings_stream(host[i % 2] for i in range(args.steps)):
+        pass
     barrier()
     e2e_s = time.perf_counter() - t0
     assert np.isfinite(out.numpy()).all()
@@ -261,7 +261,7 @@ def main():
                        "l2": "two alternating input batches; per-step working set ~2.2 GB >> 126 MB L2"},
             "e2e": {"value": world * BATCH * args.steps / e2e_s, "unit": "utterances/s",
                     "h2d_bytes_per_step": BATCH * SAMPLES * 4, "d2h_bytes_per_step": BATCH * 192 * 4,
-                    "api": "PPVectorPredictor.extract_embeddings_pinned (pinned fp32 waveforms -> embeddings on host)"},
+                    "api": "PPVectorPredictor.extract_embeddings_stream (pinned fp32 waveforms -> H2D on a copy stream overlapped with the previous batch's kernels -> embeddings on pinned host memory; every step pays its own H2D + D2H)"},
             "gpu_launches": int(g_n.value + o_n.value),
             "clocks": clk,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,

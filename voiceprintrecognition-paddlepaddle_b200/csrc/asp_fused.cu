@@ -1,0 +1,293 @@
+// Fused attentive-statistics pooling (K5): attention logits + softmax over time + weighted mean / std + asp_bn in
+// ONE kernel; the [frames, 1536] logits never exist in HBM.
+// Reference: ppvector/models/pooling.py:107-123 (attn = conv(tanh(tdnn(.))); masked softmax over T;
+// mean = sum(a x); std = sqrt(clip(sum(a (x - mean)^2), eps))) and ppvector/models/ecapa_tdnn.py:271 (asp_bn).
+//
+// The GEMM is TRANSPOSED relative to the other layers: D[channel, frame] = W2[channel, :] . att[frame, :], i.e.
+// A = conv weight slab (128 channels x K=128, K-major), B = attention-TDNN activations (128 frames x K, K-major:
+// the activation matrix is already laid out that way).  A TMEM lane is then a CHANNEL and its columns are FRAMES, so
+// each epilogue thread owns one channel and walks the frames of the utterance sequentially: the softmax over time and
+// the weighted moments are per-thread running sums -- no cross-thread reduction, no atomics, deterministic.
+//   * online softmax (running max, rescale once per 32-frame chunk)
+//   * moments about the channel's global mean g (from asp_global): S0 = sum e, S1 = sum e (x-g), S2 = sum e (x-g)^2,
+//     mean = g + S1/S0, var = S2/S0 - (S1/S0)^2   (shifted one-pass; the reference is two-pass)
+//   * the conv bias is constant over time and cancels in the softmax: it is not even loaded.
+// Work item = (utterance b, 128-channel slab); a CTA keeps the weight slab in smem for the item, streams the
+// utterance's 128-frame tiles through a 2-deep ring, double-buffers the accumulator in TMEM.
+#include <stdio.h>
+#include <string.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace ppv {
+
+constexpr int AF_TILE_BYTES = 128 * 64 * 2;  // one [128 rows x 64 k] bf16 tile, SWIZZLE_128B
+constexpr int AF_STAGES = 2;
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(256, 1) asp_fused_kernel(const __grid_constant__ AspFusedParams p) {
+    constexpr int NP = (NSPLIT == 3) ? 2 : 1;  // planes loaded per operand
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const int ksteps = p.K / 64;                       // 2 for K = 128
+    const int op_bytes = ksteps * NP * AF_TILE_BYTES;  // one operand, all K, all planes
+    const uint32_t a_base = smem_base;
+    const uint32_t b_base = smem_base + op_bytes;
+    const uint32_t bar_base = b_base + AF_STAGES * op_bytes;
+    // barriers: a_full, a_empty, b_full[2], b_empty[2], tfull[2], tempty[2], tmem slot
+    const uint32_t a_full = bar_base, a_empty = bar_base + 8;
+    auto b_full = [&](int s) { return bar_base + 16u + 8u * s; };
+    auto b_empty = [&](int s) { return bar_base + 32u + 8u * s; };
+    auto tfull = [&](int a) { return bar_base + 48u + 8u * a; };
+    auto tempty = [&](int a) { return bar_base + 64u + 8u * a; };
+    const uint32_t tmem_slot = bar_base + 80u;
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&p.mapW);
+        prefetch_tmap(&p.mapAtt);
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(a_full, 1);
+        mbar_init(a_empty, 1);
+        for (int s = 0; s < AF_STAGES; ++s) {
+            mbar_init(b_full(s), 1);
+            mbar_init(b_empty(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull(a), 1);
+            mbar_init(tempty(a), 128);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, 256);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    const int slabs = p.C / 128;
+    const int items = slabs * p.B;
+    const int ntiles = (p.T + 127) / 128;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        int stage = 0;
+        uint32_t phase = 0, a_phase = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            const int slab = item / p.B, b = item - slab * p.B;
+            mbar_wait(a_empty, a_phase ^ 1u);
+            if (lane == 0) {
+                mbar_arrive_expect_tx(a_full, op_bytes);
+                for (int ks = 0; ks < ksteps; ++ks)
+                    for (int pl = 0; pl < NP; ++pl)
+                        tma_load_3d(a_base + (ks * NP + pl) * AF_TILE_BYTES, &p.mapW, a_full, ks * 64, slab * 128, pl);
+            }
+            __syncwarp();
+            a_phase ^= 1u;
+            const int row0 = b * p.Tp + p.P;
+            for (int ft = 0; ft < ntiles; ++ft) {
+                mbar_wait(b_empty(stage), phase ^ 1u);
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(b_full(stage), op_bytes);
+                    for (int ks = 0; ks < ksteps; ++ks)
+                        for (int pl = 0; pl < NP; ++pl)
+                            tma_load_3d(b_base + stage * op_bytes + (ks * NP + pl) * AF_TILE_BYTES, &p.mapAtt, b_full(stage), ks * 64,
+                                        row0 + ft * 128, pl);
+                }
+                __syncwarp();
+                if (++stage == AF_STAGES) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = make_idesc_bf16(128, 128);
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0, a_phase = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            mbar_wait(a_full, a_phase);
+            a_phase ^= 1u;
+            for (int ft = 0; ft < ntiles; ++ft) {
+                mbar_wait(tempty(acc), acc_phase ^ 1u);
+                mbar_wait(b_full(stage), phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t d_tmem = tmem_base + acc * 128;
+                    uint32_t accumulate = 0;
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const uint64_t a_hi = make_sw128_kmajor_desc(a_base + (ks * NP) * AF_TILE_BYTES);
+                        const uint64_t b_hi = make_sw128_kmajor_desc(b_base + stage * op_bytes + (ks * NP) * AF_TILE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            umma_bf16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, accumulate);
+                            accumulate = 1;
+                        }
+                        if (NSPLIT == 3) {
+                            const uint64_t a_lo = make_sw128_kmajor_desc(a_base + (ks * NP + 1) * AF_TILE_BYTES);
+                            const uint64_t b_lo = make_sw128_kmajor_desc(b_base + stage * op_bytes + (ks * NP + 1) * AF_TILE_BYTES);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+                        }
+                    }
+                    umma_commit(b_empty(stage));
+                    umma_commit(tfull(acc));
+                    if (ft == ntiles - 1) umma_commit(a_empty);  // weight slab free once the item's MMAs retire
+                }
+                __syncwarp();
+                if (++stage == AF_STAGES) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: one thread = one channel =====================
+        const int q = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const __nv_bfloat16* xh = p.x.hi();
+        const __nv_bfloat16* xl = p.x.lo();
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            const int slab = item / p.B, b = item - slab * p.B;
+            const int c = slab * 128 + q * 32 + lane;
+            const int64_t goff = int64_t(b) * p.gstat.ld + c;
+            const float g = __bfloat162float(p.gstat.hi()[goff]) + __bfloat162float(p.gstat.lo()[goff]);
+            float m = -INFINITY, S0 = 0.f, S1 = 0.f, S2 = 0.f;
+            const int64_t row0 = int64_t(b) * p.Tp + p.P;
+            for (int ft = 0; ft < ntiles; ++ft) {
+                mbar_wait(tfull(acc), acc_phase);
+                tc_fence_after();
+                const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + acc * 128;
+#pragma unroll 1
+                for (int ch = 0; ch < 4; ++ch) {
+                    const int t0 = ft * 128 + ch * 32;
+                    uint32_t v[32];
+                    __syncwarp();
+                    tmem_ld32(t_addr + ch * 32, v);
+                    const int nvalid = min(32, p.T - t0);  // warp-uniform
+                    float xv[32];
+                    if (nvalid > 0) {
+                        const int64_t base = (row0 + t0) * p.x.ld + c;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (j < nvalid) {
+                                const int64_t o = base + int64_t(j) * p.x.ld;
+                                xv[j] = __bfloat162float(xh[o]) + __bfloat162float(xl[o]);
+                            } else {
+                                xv[j] = 0.f;
+                            }
+                        }
+                    }
+                    tmem_ld_wait();
+                    if (nvalid <= 0) continue;
+                    float cm = -INFINITY;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < nvalid) cm = fmaxf(cm, __uint_as_float(v[j]));
+                    if (cm > m) {
+                        const float r = expf(m - cm);  // exp(-inf) = 0 on the first chunk
+                        S0 *= r;
+                        S1 *= r;
+                        S2 *= r;
+                        m = cm;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (j < nvalid) {
+                            const float e = expf(__uint_as_float(v[j]) - m);
+                            const float d = xv[j] - g;
+                            S0 += e;
+                            S1 = fmaf(e, d, S1);
+                            S2 = fmaf(e * d, d, S2);
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(tempty(acc));
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+            }
+            const float inv = 1.f / S0;
+            const float dm = S1 * inv;
+            const float mean = g + dm;
+            const float sd = sqrtf(fmaxf(S2 * inv - dm * dm, p.eps));
+            const int C = p.C;
+            if (p.out_raw) {
+                p.out_raw[int64_t(b) * 2 * C + c] = mean;
+                p.out_raw[int64_t(b) * 2 * C + C + c] = sd;
+            }
+            __nv_bfloat16 h, l;
+            split_bf16(fmaf(mean, p.bn_scale[c], p.bn_shift[c]), h, l);
+            p.out.hi()[int64_t(b) * p.out.ld + c] = h;
+            p.out.lo()[int64_t(b) * p.out.ld + c] = l;
+            split_bf16(fmaf(sd, p.bn_scale[C + c], p.bn_shift[C + c]), h, l);
+            p.out.hi()[int64_t(b) * p.out.ld + C + c] = h;
+            p.out.lo()[int64_t(b) * p.out.ld + C + c] = l;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 256);
+}
+
+int asp_fused_build(AspFusedParams* p, const Planes& W, const Planes& att, const Planes& x, const Planes& gstat, const float* bn_scale,
+                    const float* bn_shift, const Planes& out, float* out_raw, int B, int T, int P, int Tp, int C, int K, float eps) {
+    PPV_REQUIRE(C % 128 == 0 && K % 64 == 0 && K <= 128, "asp_fused: C % 128 == 0 and K in {64,128} required");
+    memset(p, 0, sizeof(*p));
+    int rc = encode_planes_map(&p->mapW, W, 128);
+    if (rc) return rc;
+    rc = encode_planes_map(&p->mapAtt, att, 128);
+    if (rc) return rc;
+    p->x = x;
+    p->gstat = gstat;
+    p->bn_scale = bn_scale;
+    p->bn_shift = bn_shift;
+    p->out = out;
+    p->out_raw = out_raw;
+    p->B = B;
+    p->T = T;
+    p->P = P;
+    p->Tp = Tp;
+    p->C = C;
+    p->K = K;
+    p->eps = eps;
+    return PPV_OK;
+}
+
+int asp_fused_launch(const AspFusedParams& p, int precision, int num_sms, cudaStream_t st) {
+    const bool x3 = precision == PPV_PREC_BF16X3;
+    const int ksteps = p.K / 64;
+    const int smem = 1024 + (1 + AF_STAGES) * ksteps * (x3 ? 2 : 1) * AF_TILE_BYTES + 128;
+    static bool attr3 = false, attr1 = false;
+    bool& attr = x3 ? attr3 : attr1;
+    if (!attr) {
+        if (x3)
+            PPV_CUDA_OK(cudaFuncSetAttribute(asp_fused_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        else
+            PPV_CUDA_OK(cudaFuncSetAttribute(asp_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr = true;
+    }
+    const int items = (p.C / 128) * p.B;
+    const int grid = std::min(items, num_sms);
+    if (x3)
+        asp_fused_kernel<3><<<grid, 256, smem, st>>>(p);
+    else
+        asp_fused_kernel<1><<<grid, 256, smem, st>>>(p);
+    PPV_LAUNCH_OK("asp_fused_kernel");
+    return PPV_OK;
+}
+
+}  // namespace ppv

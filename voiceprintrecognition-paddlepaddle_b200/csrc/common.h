@@ -73,6 +73,7 @@ struct Epilogue {
     const float* bn_shift = nullptr;     // [N]
     int relu = 0;
     int tanh_ = 0;
+    int sigmoid_ = 0;
     int out_mode = OUT_PLANES;
     void* out = nullptr;            // Planes base (bf16) or float*
     int64_t out_ld = 0;             // elements
@@ -109,12 +110,30 @@ int gemm_build(GemmParams* gp, const GemmSource* srcs, int nsrc, const Planes& W
 int gemm_launch(const GemmParams& gp, int BN, int precision, int num_sms, cudaStream_t stream);
 int gemm_max_smem_setup();
 
+int encode_planes_map(CUtensorMap* m, const Planes& t, int box_rows);  // 3-D TMA map over split planes, box {64, box_rows, 1}
+
+// ---- fused attentive statistics pooling (asp_fused.cu) ----------------------------------------------
+struct AspFusedParams {
+    CUtensorMap mapW;    // planes [2][C][K]   box {64, 128, 1}
+    CUtensorMap mapAtt;  // planes [2][rows][K] box {64, 128, 1}
+    Planes x;            // MFA output, padded time layout, ld = C
+    Planes gstat;        // [B, 2C] (global mean | std): mean used as the shift
+    const float* bn_scale;  // asp_bn folded, [2C]
+    const float* bn_shift;
+    Planes out;          // [B, 2C] (mean | std) after asp_bn -> fc GEMM operand
+    float* out_raw;      // [B, 2C] fp32 before asp_bn (tap)
+    int B, T, P, Tp, C, K;
+    float eps;
+};
+
+int asp_fused_build(AspFusedParams* p, const Planes& W, const Planes& att, const Planes& x, const Planes& gstat, const float* bn_scale,
+                    const float* bn_shift, const Planes& out, float* out_raw, int B, int T, int P, int Tp, int C, int K, float eps);
+int asp_fused_launch(const AspFusedParams& p, int precision, int num_sms, cudaStream_t st);
+
 // ---- other kernels (elementwise.cu) ---------------------------------------------------------------
 int launch_pack_features(const float* feat, int B, int T, int F, const Planes& out, int P, int Tp, cudaStream_t st);
 int launch_colstats(const Planes& x, int col0, int C, int B, int T, int P, int Tp, int mode, float eps, float* out_f32,
                     const Planes& out_pl, cudaStream_t st);
-int launch_se_excite(const float* mean, const float* W1, const float* b1, const float* W2, const float* b2, int B, int C,
-                     int S, float* scale, cudaStream_t st);
 int launch_se_scale_res(const Planes& z, const float* scale, const Planes& res, int rc0, const Planes& out, int oc0, int C,
                         int Tp, int64_t rows, int num_sms, cudaStream_t st);
 int launch_asp_pool(const float* logits, int64_t lg_ld, const Planes& x, int C, int B, int T, int P, int Tp, float eps,

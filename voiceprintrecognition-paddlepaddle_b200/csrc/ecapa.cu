@@ -41,11 +41,12 @@ struct KSpec {  // one K group: `ncols` columns of a source at a row offset <- w
     int w_cin0, w_cnt, w_tap;
 };
 
-enum Buf { B_FEAT, B_X0, B_H, B_Y, B_Z, B_CAT, B_MFA, B_ATT, B_GSTAT, B_POOL, B_COUNT };
+enum Buf { B_FEAT, B_X0, B_H, B_Y, B_Z, B_CAT, B_MFA, B_ATT, B_GSTAT, B_POOL, B_SEM, B_SEH, B_COUNT };
 
 struct Step {
-    enum Kind { GEMM, SE_SQUEEZE, SE_EXCITE, SE_SCALE, ASP_GLOBAL, ASP_POOL } kind;
+    enum Kind { GEMM, SE_SQUEEZE, SE_SCALE, ASP_GLOBAL, ASP_FUSED } kind;
     GemmParams gp;
+    AspFusedParams ap;
     int BN = 0;
     int blk = 0;  // block index for the SE steps
 };
@@ -64,8 +65,7 @@ struct EcapaModel {
     // device weights
     void* arena = nullptr;
     size_t arena_bytes = 0, arena_used = 0;
-    ConvW conv0, tdnn1[3], res2[3][8], tdnn2[3], mfa, fold, att1, att2, fc;
-    float *se_w1[3] = {}, *se_b1[3] = {}, *se_w2[3] = {}, *se_b2[3] = {};
+    ConvW conv0, tdnn1[3], res2[3][8], tdnn2[3], se1[3], se2[3], mfa, fold, att1, att2, fc;
     float *aspbn_scale = nullptr, *aspbn_shift = nullptr;
     // plan
     std::vector<Step> steps;
@@ -97,8 +97,8 @@ int ecapa_create(const ppv_ecapa_cfg* cfg, EcapaModel** out) {
     if (cfg->kernel_sizes[1] != 3 || cfg->kernel_sizes[2] != 3 || cfg->kernel_sizes[3] != 3 || cfg->kernel_sizes[4] != 1 ||
         (cfg->kernel_sizes[0] % 2) == 0 || cfg->dilations[4] != 1)
         return fail(PPV_EUNSUPPORTED, "ecapa: kernel sizes must be [odd,3,3,3,1]");
-    if (cfg->attention_channels % 64 || cfg->embd_dim % 32 || cfg->se_channels <= 0)
-        return fail(PPV_EUNSUPPORTED, "ecapa: attention_channels % 64, embd_dim % 32 required");
+    if (cfg->attention_channels % 64 || cfg->embd_dim % 32 || cfg->se_channels <= 0 || cfg->se_channels % 64)
+        return fail(PPV_EUNSUPPORTED, "ecapa: attention_channels % 64, se_channels % 64, embd_dim % 32 required");
     EcapaModel* m = new EcapaModel();
     m->cfg = *cfg;
     m->precision = cfg->precision;
@@ -291,17 +291,9 @@ int ecapa_finalize(EcapaModel* m) {
         }
         ok = ok && conv_layer(&m->tdnn2[b - 1], p + ".tdnn2.conv.conv", C, C, 1, {{B_H, 0, w, 0, 0, w, 0}, {B_Y, w, C - w, 0, w, C - w, 0}},
                               p + ".tdnn2.norm.norm", true);
-        if (ok) {
-            const HostW *w1 = f.get(p + ".se_block.conv1.conv.weight", {S, C, 1}), *b1 = f.get(p + ".se_block.conv1.conv.bias", {S}),
-                        *w2 = f.get(p + ".se_block.conv2.conv.weight", {C, S, 1}), *b2 = f.get(p + ".se_block.conv2.conv.bias", {C});
-            ok = w1 && b1 && w2 && b2;
-            if (ok) {
-                put_vec(&m->se_w1[b - 1], w1->v);
-                put_vec(&m->se_b1[b - 1], b1->v);
-                put_vec(&m->se_w2[b - 1], w2->v);
-                put_vec(&m->se_b2[b - 1], b2->v);
-            }
-        }
+        // SE excitation as two small gather-GEMMs over the [B, C] squeeze (ecapa_tdnn.py:79-80)
+        ok = ok && conv_layer(&m->se1[b - 1], p + ".se_block.conv1.conv", S, C, 1, {{B_SEM, 0, C, 0, 0, C, 0}}, "", true);
+        ok = ok && conv_layer(&m->se2[b - 1], p + ".se_block.conv2.conv", C, S, 1, {{B_SEH, 0, S, 0, 0, S, 0}}, "", true);
     }
     ok = ok && conv_layer(&m->mfa, "mfa.conv.conv", C3, C3, 1, {{B_CAT, 0, C3, 0, 0, C3, 0}}, "mfa.norm.norm", true);
     // ASP attention TDNN: weight [A, 3*C3, 1] split into the x part (cols 0..C3) and the [mean;std] part
@@ -368,10 +360,11 @@ void carve(EcapaModel* m, Carver& cv, int B, int T) {
     m->bufs[B_ATT] = cv.planes(R, m->att);
     m->bufs[B_GSTAT] = cv.planes(B, 2 * C3);
     m->bufs[B_POOL] = cv.planes(B, 2 * C3);
+    m->bufs[B_SEM] = cv.planes(B, C);
+    m->bufs[B_SEH] = cv.planes(B, m->se);
     m->se_mean = static_cast<float*>(cv.take(size_t(B) * C * 4));
     m->se_scale = static_cast<float*>(cv.take(size_t(B) * C * 4));
     m->fold_out = static_cast<float*>(cv.take(size_t(align_up(B, 128)) * m->att * 4));
-    m->logits = static_cast<float*>(cv.take(size_t(align_up(size_t(R), 128)) * C3 * 4));
     m->pooled_raw = static_cast<float*>(cv.take(size_t(B) * 2 * C3 * 4));
     m->raw_logmel = static_cast<float*>(cv.take(size_t(B) * T * m->cfg.input_size * 4));
     m->emb_out = static_cast<float*>(cv.take(size_t(align_up(B, 128)) * m->cfg.embd_dim * 4));
@@ -467,8 +460,23 @@ static int build_plan(EcapaModel* m, int B, int T, void* ws, size_t ws_bytes, cu
         s.blk = b;
         s.kind = Step::SE_SQUEEZE;
         m->steps.push_back(s);
-        s.kind = Step::SE_EXCITE;
-        m->steps.push_back(s);
+        {  // s = sigmoid(W2 relu(W1 mean + b1) + b2): [B,C] -> [B,S] -> [B,C], plain (un-padded) row layout
+            Epilogue e1;
+            e1.out_mode = OUT_PLANES;
+            e1.out = m->bufs[B_SEH].base;
+            e1.out_ld = m->bufs[B_SEH].ld;
+            e1.out_plane_stride = m->bufs[B_SEH].plane_stride;
+            e1.relu = 1;
+            rc = add_gemm(m->se1[b - 1], {{B_SEM, 0, C, 0, 0, 0, 0}}, nullptr, 0, B, e1);
+            if (rc) return rc;
+            Epilogue e2;
+            e2.out_mode = OUT_F32;
+            e2.out = m->se_scale;
+            e2.out_ld = C;
+            e2.sigmoid_ = 1;
+            rc = add_gemm(m->se2[b - 1], {{B_SEH, 0, m->se, 0, 0, 0, 0}}, nullptr, 0, B, e2);
+            if (rc) return rc;
+        }
         s.kind = Step::SE_SCALE;
         m->steps.push_back(s);
     }
@@ -496,20 +504,12 @@ static int build_plan(EcapaModel* m, int B, int T, void* ws, size_t ws_bytes, cu
         rc = add_gemm(m->att1, {{B_MFA, 0, C3, 0, 0, 0, 0}}, nullptr, 0, int(R), ep);
         if (rc) return rc;
     }
-    {  // attention logits, fp32
-        Epilogue ep;
-        ep.out_mode = OUT_F32;
-        ep.out = m->logits;
-        ep.out_ld = C3;
-        ep.Tp = Tp;
-        ep.P = P;
-        ep.T = T;
-        rc = add_gemm(m->att2, {{B_ATT, 0, m->att, 0, 0, 0, 0}}, nullptr, 0, int(R), ep);
-        if (rc) return rc;
-    }
-    {
+    {  // attention logits (transposed GEMM) + softmax over time + weighted mean / std + asp_bn, fused
         Step s;
-        s.kind = Step::ASP_POOL;
+        s.kind = Step::ASP_FUSED;
+        rc = asp_fused_build(&s.ap, m->att2.W, m->bufs[B_ATT], m->bufs[B_MFA], m->bufs[B_GSTAT], m->aspbn_scale, m->aspbn_shift,
+                             m->bufs[B_POOL], m->pooled_raw, B, T, P, Tp, C3, m->att, 1e-12f);
+        if (rc) return rc;
         m->steps.push_back(s);
     }
     {  // fc: [B, 2*C3] -> [B, embd]
@@ -577,16 +577,13 @@ int ecapa_forward(EcapaModel* m, const float* feat, Fbank* fb, const float* wav,
     prof_mark(1, false);
     if (rc) return rc;
     for (const Step& s : m->steps) {
-        prof_mark(s.kind == Step::GEMM ? 0 : 1, true);
-        if (s.kind == Step::GEMM) m->launches_gemm += 1; else m->launches_other += 1;
+        const bool tensor_step = (s.kind == Step::GEMM || s.kind == Step::ASP_FUSED);
+        prof_mark(tensor_step ? 0 : 1, true);
+        if (tensor_step) m->launches_gemm += 1; else m->launches_other += 1;
         switch (s.kind) {
             case Step::GEMM: rc = gemm_launch(s.gp, s.BN, m->precision, m->num_sms, st); break;
             case Step::SE_SQUEEZE:
-                rc = launch_colstats(m->bufs[B_Z], 0, C, B, T, P, Tp, 0, 0.f, m->se_mean, Planes(), st);
-                break;
-            case Step::SE_EXCITE:
-                rc = launch_se_excite(m->se_mean, m->se_w1[s.blk - 1], m->se_b1[s.blk - 1], m->se_w2[s.blk - 1],
-                                      m->se_b2[s.blk - 1], B, C, m->se, m->se_scale, st);
+                rc = launch_colstats(m->bufs[B_Z], 0, C, B, T, P, Tp, 0, 0.f, nullptr, m->bufs[B_SEM], st);
                 break;
             case Step::SE_SCALE: {
                 const Planes& X = (s.blk == 1) ? m->bufs[B_X0] : m->bufs[B_CAT];
@@ -597,9 +594,8 @@ int ecapa_forward(EcapaModel* m, const float* feat, Fbank* fb, const float* wav,
             case Step::ASP_GLOBAL:
                 rc = launch_colstats(m->bufs[B_MFA], 0, C3, B, T, P, Tp, 1, 1e-12f, nullptr, m->bufs[B_GSTAT], st);
                 break;
-            case Step::ASP_POOL:
-                rc = launch_asp_pool(m->logits, C3, m->bufs[B_MFA], C3, B, T, P, Tp, 1e-12f, m->aspbn_scale, m->aspbn_shift,
-                                     m->bufs[B_POOL], m->pooled_raw, st);
+            case Step::ASP_FUSED:
+                rc = asp_fused_launch(s.ap, m->precision, m->num_sms, st);
                 break;
         }
         prof_mark(0, false);

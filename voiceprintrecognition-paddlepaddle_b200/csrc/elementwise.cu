@@ -1,7 +1,7 @@
 // HBM-bound kernels between the tensor-core GEMMs of the ECAPA-TDNN path:
 //   pack_features   [B,T,F] fp32 -> split-bf16 planes in the padded time layout (+ reflect halo)
 //   se_squeeze      SEBlock mean over time            (ppvector/models/ecapa_tdnn.py:69-78)
-//   se_excite       SEBlock conv1-ReLU-conv2-sigmoid  (ecapa_tdnn.py:79-80)
+//   (SE excite = two small gather-GEMMs with ReLU / sigmoid epilogues, see ecapa.cu)
 //   se_scale_res    s * x + residual                  (ecapa_tdnn.py:82, :142)
 //   asp_global      global mean / std of ASP          (ppvector/models/pooling.py:89-92, 102-104)
 //   asp_pool        masked softmax over time + weighted mean / std + asp_bn (pooling.py:115-123,
@@ -80,87 +80,104 @@ __device__ __forceinline__ float2 block_colsum(float2 v, float2 (*s_part)[32], i
     return r;
 }
 
-// mode 0: mean only -> out_f32[b, C]            (SE squeeze)
-// mode 1: mean and std = sqrt(clip(sum((x-mean)^2)/T, eps)) -> planes [B, 2C] (mean | std)  (ASP global context)
+// mode 0: mean -> out_f32[b, C] and/or planes [B, C]                                  (SE squeeze)
+// mode 1: mean and std = sqrt(clip(var, eps)) -> planes [B, 2C] (mean | std)             (ASP global context)
+// Single pass with a per-channel shift K = x[first frame]: sum(x-K), sum((x-K)^2); var = (Q - S^2/T)/T.
+// Each lane owns 8 channels (one 16-byte load per plane), 4 frames per warp, 32 frames per block iteration.
 __global__ void __launch_bounds__(STAT_WARPS * 32)
     colstats_kernel(Planes x, int col0, int C, int T, int P, int Tp, int mode, float eps, float* __restrict__ out_f32,
                     Planes out_pl) {
-    __shared__ float2 s_part[STAT_WARPS][32];
+    __shared__ float s_s[STAT_WARPS][64];
+    __shared__ float s_q[STAT_WARPS][64];
     const int b = blockIdx.y;
-    const int c = col0 + blockIdx.x * 64 + 2 * (threadIdx.x & 31);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cg = lane & 7, rsub = lane >> 3;
+    const int c = col0 + blockIdx.x * 64 + cg * 8;
     const int64_t row0 = int64_t(b) * Tp + P;
-    float2 acc = make_float2(0.f, 0.f);
-    for (int t = warp; t < T; t += STAT_WARPS) {
-        const float2 v = ld_split2(x.hi(), x.lo(), (row0 + t) * x.ld + c);
-        acc.x += v.x;
-        acc.y += v.y;
+    auto load8 = [&](int64_t row, float (&v)[8]) {
+        const uint4 h = *reinterpret_cast<const uint4*>(x.hi() + row * x.ld + c);
+        const uint4 l = *reinterpret_cast<const uint4*>(x.lo() + row * x.ld + c);
+        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[i]));
+            const float2 lf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&lw[i]));
+            v[2 * i] = hf.x + lf.x;
+            v[2 * i + 1] = hf.y + lf.y;
+        }
+    };
+    float k[8], s[8], q[8];
+    load8(row0, k);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+#pragma unroll 2
+    for (int t = warp * 4 + rsub; t < T; t += STAT_WARPS * 4) {
+        float v[8];
+        load8(row0 + t, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float d = v[i] - k[i];
+            s[i] += d;
+            q[i] = fmaf(d, d, q[i]);
+        }
     }
-    float2 sum = block_colsum(acc, s_part, warp, lane);
-    const float inv = 1.f / float(T);
-    const float2 mean = make_float2(sum.x * inv, sum.y * inv);
-    const int cc = blockIdx.x * 64 + 2 * lane;  // channel index relative to col0
-    if (mode == 0) {
-        if (warp == 0) *reinterpret_cast<float2*>(out_f32 + int64_t(b) * C + cc) = mean;
-        return;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        s[i] += __shfl_xor_sync(0xffffffffu, s[i], 8);
+        s[i] += __shfl_xor_sync(0xffffffffu, s[i], 16);
+        q[i] += __shfl_xor_sync(0xffffffffu, q[i], 8);
+        q[i] += __shfl_xor_sync(0xffffffffu, q[i], 16);
     }
-    acc = make_float2(0.f, 0.f);
-    for (int t = warp; t < T; t += STAT_WARPS) {
-        const float2 v = ld_split2(x.hi(), x.lo(), (row0 + t) * x.ld + c);
-        const float dx = v.x - mean.x, dy = v.y - mean.y;
-        acc.x += dx * dx;
-        acc.y += dy * dy;
+    if (rsub == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            s_s[warp][cg * 8 + i] = s[i];
+            s_q[warp][cg * 8 + i] = q[i];
+        }
     }
-    sum = block_colsum(acc, s_part, warp, lane);
-    if (warp == 0) {
-        const float sx = sqrtf(fmaxf(sum.x * inv, eps)), sy = sqrtf(fmaxf(sum.y * inv, eps));
-        st_split2(out_pl.hi(), out_pl.lo(), int64_t(b) * out_pl.ld + cc, mean.x, mean.y);
-        st_split2(out_pl.hi(), out_pl.lo(), int64_t(b) * out_pl.ld + C + cc, sx, sy);
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        const int ch = threadIdx.x;  // channel within the slab
+        float S = 0.f, Q = 0.f;
+#pragma unroll
+        for (int w = 0; w < STAT_WARPS; ++w) {
+            S += s_s[w][ch];
+            Q += s_q[w][ch];
+        }
+        // shift of this channel: lane (ch / 8) of warp 0 holds k[ch % 8]; re-read instead of shuffling
+        const int64_t off0 = row0 * x.ld + col0 + blockIdx.x * 64 + ch;
+        const float K = __bfloat162float(x.hi()[off0]) + __bfloat162float(x.lo()[off0]);
+        const float inv = 1.f / float(T);
+        const float mean = K + S * inv;
+        const int cc = blockIdx.x * 64 + ch;
+        if (mode == 0) {
+            if (out_f32) out_f32[int64_t(b) * C + cc] = mean;
+            if (out_pl.base) {
+                __nv_bfloat16 h, l;
+                split_bf16(mean, h, l);
+                out_pl.hi()[int64_t(b) * out_pl.ld + cc] = h;
+                out_pl.lo()[int64_t(b) * out_pl.ld + cc] = l;
+            }
+        } else {
+            const float var = (Q - S * S * inv) * inv;
+            const float sd = sqrtf(fmaxf(var, eps));
+            __nv_bfloat16 h, l;
+            split_bf16(mean, h, l);
+            out_pl.hi()[int64_t(b) * out_pl.ld + cc] = h;
+            out_pl.lo()[int64_t(b) * out_pl.ld + cc] = l;
+            split_bf16(sd, h, l);
+            out_pl.hi()[int64_t(b) * out_pl.ld + C + cc] = h;
+            out_pl.lo()[int64_t(b) * out_pl.ld + C + cc] = l;
+        }
     }
 }
 
 int launch_colstats(const Planes& x, int col0, int C, int B, int T, int P, int Tp, int mode, float eps, float* out_f32,
                     const Planes& out_pl, cudaStream_t st) {
-    PPV_REQUIRE(C % 64 == 0, "colstats: C must be a multiple of 64");
+    PPV_REQUIRE(C % 64 == 0 && col0 % 8 == 0 && x.ld % 8 == 0, "colstats: C % 64, col0 % 8, ld % 8 required");
     dim3 grid(C / 64, B);
     colstats_kernel<<<grid, STAT_WARPS * 32, 0, st>>>(x, col0, C, T, P, Tp, mode, eps, out_f32, out_pl);
     PPV_LAUNCH_OK("colstats_kernel");
-    return PPV_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
-// SE excitation: s = sigmoid(W2 relu(W1 m + b1) + b2), one block per utterance.  W1 [S,C], W2 [C,S] fp32.
-__global__ void __launch_bounds__(256)
-    se_excite_kernel(const float* __restrict__ mean, const float* __restrict__ W1, const float* __restrict__ b1,
-                     const float* __restrict__ W2, const float* __restrict__ b2, int C, int S, float* __restrict__ scale) {
-    extern __shared__ float sm[];
-    float* s_m = sm;      // [C]
-    float* s_h = sm + C;  // [S]
-    const int b = blockIdx.x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < C; i += blockDim.x) s_m[i] = mean[int64_t(b) * C + i];
-    __syncthreads();
-    for (int j = warp; j < S; j += 8) {
-        const float* w = W1 + int64_t(j) * C;
-        float a = 0.f;
-        for (int i = lane; i < C; i += 32) a = fmaf(w[i], s_m[i], a);
-        a = warp_sum(a);
-        if (lane == 0) s_h[j] = fmaxf(a + b1[j], 0.f);
-    }
-    __syncthreads();
-    for (int j = warp; j < C; j += 8) {
-        const float* w = W2 + int64_t(j) * S;
-        float a = 0.f;
-        for (int i = lane; i < S; i += 32) a = fmaf(w[i], s_h[i], a);
-        a = warp_sum(a);
-        if (lane == 0) scale[int64_t(b) * C + j] = 1.f / (1.f + expf(-(a + b2[j])));
-    }
-}
-
-int launch_se_excite(const float* mean, const float* W1, const float* b1, const float* W2, const float* b2, int B, int C,
-                     int S, float* scale, cudaStream_t st) {
-    se_excite_kernel<<<B, 256, (C + S) * sizeof(float), st>>>(mean, W1, b1, W2, b2, C, S, scale);
-    PPV_LAUNCH_OK("se_excite_kernel");
     return PPV_OK;
 }
 

@@ -245,6 +245,10 @@ __global__ void __launch_bounds__(256, 1) gemm_tcgen05_kernel(const __grid_const
 #pragma unroll
                     for (int j = 0; j < 32; ++j) x[j] = tanhf(x[j]);
                 }
+                if (ep.sigmoid_) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] = 1.f / (1.f + expf(-x[j]));
+                }
                 if (ep.out_mode == OUT_F32) {
                     float* dstf = static_cast<float*>(ep.out) + row * ep.out_ld + ep.out_col0 + col;
                     if (ep.f32_vec_ok && col + 32 <= gp.N) {
@@ -312,7 +316,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 3-D map over split planes [2][rows][ld] bf16, box = {64 cols, box_rows, 1 plane}, SWIZZLE_128B.
-static int encode_planes_map(CUtensorMap* m, const Planes& t, int box_rows) {
+int encode_planes_map(CUtensorMap* m, const Planes& t, int box_rows) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return fail(PPV_ECUDA, "cuTensorMapEncodeTiled entry point not available");
     if ((reinterpret_cast<uintptr_t>(t.base) & 15) || (t.ld % 8) || (t.plane_stride % 8))

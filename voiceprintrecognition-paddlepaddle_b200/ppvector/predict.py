@@ -104,6 +104,53 @@ class PPVectorPredictor:
         torch.cuda.current_stream().synchronize()
         return out
 
+    def extract_embeddings_stream(self, pinned_batches, input_lens_ratio=None):
+        """Pipelined form of extract_embeddings_pinned for a sequence of pinned [B,L] float32 host batches: the H2D
+        copy of batch i+1 runs on a copy stream while batch i is in the kernels (two device staging buffers, events
+        in both directions).  Yields one pinned host [B,embd] tensor per batch, in order; every batch still pays its
+        own H2D and D2H -- they are overlapped, not skipped."""
+        comp = torch.cuda.current_stream(self.device)
+        copy = getattr(self, '_copy_stream', None)
+        if copy is None:
+            copy = self._copy_stream = torch.cuda.Stream(self.device)
+        dev = [None, None]
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        free = [torch.cuda.Event(), torch.cuda.Event()]
+        done = [torch.cuda.Event(), torch.cuda.Event()]
+        outs = [None, None]
+        it = iter(pinned_batches)
+
+        def stage(i, host):
+            k = i & 1
+            with torch.cuda.stream(copy):
+                if i >= 2:
+                    copy.wait_event(free[k])  # the kernels of batch i-2 have consumed this buffer
+                if dev[k] is None or dev[k].shape != host.shape:
+                    dev[k] = torch.empty(host.shape, dtype=torch.float32, device=self.device)
+                dev[k].copy_(host, non_blocking=True)
+                ready[k].record(copy)
+
+        nxt = next(it, None)
+        if nxt is None:
+            return
+        stage(0, nxt)
+        i = 0
+        while nxt is not None:
+            k = i & 1
+            comp.wait_event(ready[k])
+            emb = self.predictor.forward_wav(self._audio_featurizer, dev[k], input_lens_ratio)
+            free[k].record(comp)
+            if outs[k] is None or outs[k].shape != emb.shape:
+                outs[k] = torch.empty(emb.shape, dtype=torch.float32).pin_memory()
+            outs[k].copy_(emb, non_blocking=True)
+            done[k].record(comp)
+            nxt = next(it, None)
+            if nxt is not None:
+                stage(i + 1, nxt)  # overlaps with the kernels just enqueued
+            done[k].synchronize()
+            yield outs[k]
+            i += 1
+
     def predict(self, audio_data, sample_rate=16000):
         """reference: predict.py:218-233 -> [embd] numpy"""
         seg = self._load_audio(audio_data=audio_data, sample_rate=sample_rate)
