@@ -12,8 +12,10 @@
 //   * moments about the channel's global mean g (from asp_global): S0 = sum e, S1 = sum e (x-g), S2 = sum e (x-g)^2,
 //     mean = g + S1/S0, var = S2/S0 - (S1/S0)^2   (shifted one-pass; the reference is two-pass)
 //   * the conv bias is constant over time and cancels in the softmax: it is not even loaded.
-// Work item = (utterance b, 128-channel slab); a CTA keeps the weight slab in smem for the item, streams the
-// utterance's 128-frame tiles through a 2-deep ring, double-buffers the accumulator in TMEM.
+// Work item = (utterance b, 128-channel slab); a CTA keeps the weight slab in smem for the item and streams the
+// utterance in 64-frame tiles through a 2-deep TMA ring.  A ring stage carries BOTH the attention activations (the
+// MMA's B operand) and the matching [64 frames x 128 channels] tile of x (un-swizzled, read by the epilogue with
+// plain ld.shared), so the epilogue never waits on global memory; the accumulator is double-buffered in TMEM.
 #include <stdio.h>
 #include <string.h>
 
@@ -22,20 +24,25 @@
 
 namespace ppv {
 
-constexpr int AF_TILE_BYTES = 128 * 64 * 2;  // one [128 rows x 64 k] bf16 tile, SWIZZLE_128B
+constexpr int AF_NT = 64;                         // frames per tile (MMA N)
+constexpr int AF_A_TILE = 128 * 64 * 2;           // weight tile  [128 ch x 64 k]  bf16, SWIZZLE_128B
+constexpr int AF_B_TILE = AF_NT * 64 * 2;         // att tile     [64 fr x 64 k]   bf16, SWIZZLE_128B
+constexpr int AF_X_TILE = AF_NT * 128 * 2;        // x tile       [64 fr x 128 ch] bf16, no swizzle (one plane)
 constexpr int AF_STAGES = 2;
 
 template <int NSPLIT>
 __global__ void __launch_bounds__(256, 1) asp_fused_kernel(const __grid_constant__ AspFusedParams p) {
-    constexpr int NP = (NSPLIT == 3) ? 2 : 1;  // planes loaded per operand
+    constexpr int NP = (NSPLIT == 3) ? 2 : 1;  // planes loaded per MMA operand
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-    const int ksteps = p.K / 64;                       // 2 for K = 128
-    const int op_bytes = ksteps * NP * AF_TILE_BYTES;  // one operand, all K, all planes
+    const int ksteps = p.K / 64;  // 2 for K = 128
+    const int a_bytes = ksteps * NP * AF_A_TILE;
+    const int b_bytes = ksteps * NP * AF_B_TILE;
+    const int stage_bytes = b_bytes + 2 * AF_X_TILE;  // x always needs hi and lo
     const uint32_t a_base = smem_base;
-    const uint32_t b_base = smem_base + op_bytes;
-    const uint32_t bar_base = b_base + AF_STAGES * op_bytes;
+    const uint32_t s_base = smem_base + a_bytes;
+    const uint32_t bar_base = s_base + AF_STAGES * stage_bytes;
     // barriers: a_full, a_empty, b_full[2], b_empty[2], tfull[2], tempty[2], tmem slot
     const uint32_t a_full = bar_base, a_empty = bar_base + 8;
     auto b_full = [&](int s) { return bar_base + 16u + 8u * s; };
@@ -49,13 +56,14 @@ __global__ void __launch_bounds__(256, 1) asp_fused_kernel(const __grid_constant
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&p.mapW);
         prefetch_tmap(&p.mapAtt);
+        prefetch_tmap(&p.mapX);
     }
     if (warp == 1 && lane == 0) {
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
         for (int s = 0; s < AF_STAGES; ++s) {
             mbar_init(b_full(s), 1);
-            mbar_init(b_empty(s), 1);
+            mbar_init(b_empty(s), 1 + 128);  // MMA commit + the 128 epilogue threads that read the x tile
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull(a), 1);
@@ -64,7 +72,7 @@ __global__ void __launch_bounds__(256, 1) asp_fused_kernel(const __grid_constant
         fence_mbar_init();
     }
     if (warp == 2) {
-        tmem_alloc(tmem_slot, 256);
+        tmem_alloc(tmem_slot, 128);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -74,7 +82,7 @@ __global__ void __launch_bounds__(256, 1) asp_fused_kernel(const __grid_constant
 
     const int slabs = p.C / 128;
     const int items = slabs * p.B;
-    const int ntiles = (p.T + 127) / 128;
+    const int ntiles = (p.T + AF_NT - 1) / AF_NT;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -84,10 +92,10 @@ __global__ void __launch_bounds__(256, 1) asp_fused_kernel(const __grid_constant
             const int slab = item / p.B, b = item - slab * p.B;
             mbar_wait(a_empty, a_phase ^ 1u);
             if (lane == 0) {
-                mbar_arrive_expect_tx(a_full, op_bytes);
+                mbar_arrive_expect_tx(a_full, a_bytes);
                 for (int ks = 0; ks < ksteps; ++ks)
                     for (int pl = 0; pl < NP; ++pl)
-                        tma_load_3d(a_base + (ks * NP + pl) * AF_TILE_BYTES, &p.mapW, a_full, ks * 64, slab * 128, pl);
+                        tma_load_3d(a_base + (ks * NP + pl) * AF_A_TILE, &p.mapW, a_full, ks * 64, slab * 128, pl);
             }
             __syncwarp();
             a_phase ^= 1u;
@@ -95,11 +103,13 @@ __global__ void __launch_bounds__(256, 1) asp_fused_kernel(const __grid_constant
             for (int ft = 0; ft < ntiles; ++ft) {
                 mbar_wait(b_empty(stage), phase ^ 1u);
                 if (lane == 0) {
-                    mbar_arrive_expect_tx(b_full(stage), op_bytes);
+                    const uint32_t sb = s_base + stage * stage_bytes;
+                    mbar_arrive_expect_tx(b_full(stage), stage_bytes);
                     for (int ks = 0; ks < ksteps; ++ks)
                         for (int pl = 0; pl < NP; ++pl)
-                            tma_load_3d(b_base + stage * op_bytes + (ks * NP + pl) * AF_TILE_BYTES, &p.mapAtt, b_full(stage), ks * 64,
-                                        row0 + ft * 128, pl);
+                            tma_load_3d(sb + (ks * NP + pl) * AF_B_TILE, &p.mapAtt, b_full(stage), ks * 64, row0 + ft * AF_NT, pl);
+                    for (int pl = 0; pl < 2; ++pl)
+                        tma_load_3d(sb + b_bytes + pl * AF_X_TILE, &p.mapX, b_full(stage), slab * 128, row0 + ft * AF_NT, pl);
                 }
                 __syncwarp();
                 if (++stage == AF_STAGES) {
@@ -110,7 +120,7 @@ __global__ void __launch_bounds__(256, 1) asp_fused_kernel(const __grid_constant
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = make_idesc_bf16(128, 128);
+        constexpr uint32_t idesc = make_idesc_bf16(128, AF_NT);
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0, a_phase = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
@@ -121,26 +131,27 @@ __global__ void __launch_bounds__(256, 1) asp_fused_kernel(const __grid_constant
                 mbar_wait(b_full(stage), phase);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t d_tmem = tmem_base + acc * 128;
+                    const uint32_t d_tmem = tmem_base + acc * AF_NT;
+                    const uint32_t sb = s_base + stage * stage_bytes;
                     uint32_t accumulate = 0;
                     for (int ks = 0; ks < ksteps; ++ks) {
-                        const uint64_t a_hi = make_sw128_kmajor_desc(a_base + (ks * NP) * AF_TILE_BYTES);
-                        const uint64_t b_hi = make_sw128_kmajor_desc(b_base + stage * op_bytes + (ks * NP) * AF_TILE_BYTES);
+                        const uint64_t a_hi = make_sw128_kmajor_desc(a_base + (ks * NP) * AF_A_TILE);
+                        const uint64_t b_hi = make_sw128_kmajor_desc(sb + (ks * NP) * AF_B_TILE);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             umma_bf16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, accumulate);
                             accumulate = 1;
                         }
                         if (NSPLIT == 3) {
-                            const uint64_t a_lo = make_sw128_kmajor_desc(a_base + (ks * NP + 1) * AF_TILE_BYTES);
-                            const uint64_t b_lo = make_sw128_kmajor_desc(b_base + stage * op_bytes + (ks * NP + 1) * AF_TILE_BYTES);
+                            const uint64_t a_lo = make_sw128_kmajor_desc(a_base + (ks * NP + 1) * AF_A_TILE);
+                            const uint64_t b_lo = make_sw128_kmajor_desc(sb + (ks * NP + 1) * AF_B_TILE);
 #pragma unroll
                             for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
 #pragma unroll
                             for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
                         }
                     }
-                    umma_commit(b_empty(stage));
+                    umma_commit(b_empty(stage));  // one of the 129 arrivals: the att tiles are consumed
                     umma_commit(tfull(acc));
                     if (ft == ntiles - 1) umma_commit(a_empty);  // weight slab free once the item's MMAs retire
                 }
@@ -156,42 +167,30 @@ __global__ void __launch_bounds__(256, 1) asp_fused_kernel(const __grid_constant
     } else if (warp >= 4) {
         // ===================== epilogue: one thread = one channel =====================
         const int q = warp & 3;
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        const __nv_bfloat16* xh = p.x.hi();
-        const __nv_bfloat16* xl = p.x.lo();
+        const int cl = q * 32 + lane;  // channel within the slab == TMEM lane
+        int acc = 0, stage = 0;
+        uint32_t acc_phase = 0, phase = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
             const int slab = item / p.B, b = item - slab * p.B;
-            const int c = slab * 128 + q * 32 + lane;
+            const int c = slab * 128 + cl;
             const int64_t goff = int64_t(b) * p.gstat.ld + c;
             const float g = __bfloat162float(p.gstat.hi()[goff]) + __bfloat162float(p.gstat.lo()[goff]);
             float m = -INFINITY, S0 = 0.f, S1 = 0.f, S2 = 0.f;
-            const int64_t row0 = int64_t(b) * p.Tp + p.P;
             for (int ft = 0; ft < ntiles; ++ft) {
+                mbar_wait(b_full(stage), phase);  // acquire the TMA-written x tile directly (already complete by now)
                 mbar_wait(tfull(acc), acc_phase);
                 tc_fence_after();
-                const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + acc * 128;
+                const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + acc * AF_NT;
+                const __nv_bfloat16* xs_hi = reinterpret_cast<const __nv_bfloat16*>(smem_gen + (s_base - smem_base) + stage * stage_bytes + b_bytes);
+                const __nv_bfloat16* xs_lo = xs_hi + AF_X_TILE / 2;
 #pragma unroll 1
-                for (int ch = 0; ch < 4; ++ch) {
-                    const int t0 = ft * 128 + ch * 32;
+                for (int ch = 0; ch < AF_NT / 32; ++ch) {
+                    const int t0 = ft * AF_NT + ch * 32;
                     uint32_t v[32];
                     __syncwarp();
                     tmem_ld32(t_addr + ch * 32, v);
-                    const int nvalid = min(32, p.T - t0);  // warp-uniform
-                    float xv[32];
-                    if (nvalid > 0) {
-                        const int64_t base = (row0 + t0) * p.x.ld + c;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (j < nvalid) {
-                                const int64_t o = base + int64_t(j) * p.x.ld;
-                                xv[j] = __bfloat162float(xh[o]) + __bfloat162float(xl[o]);
-                            } else {
-                                xv[j] = 0.f;
-                            }
-                        }
-                    }
                     tmem_ld_wait();
+                    const int nvalid = min(32, p.T - t0);  // warp-uniform
                     if (nvalid <= 0) continue;
                     float cm = -INFINITY;
 #pragma unroll
@@ -207,8 +206,10 @@ __global__ void __launch_bounds__(256, 1) asp_fused_kernel(const __grid_constant
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         if (j < nvalid) {
+                            const int o = (ch * 32 + j) * 128 + cl;
+                            const float xv = __bfloat162float(xs_hi[o]) + __bfloat162float(xs_lo[o]);
                             const float e = expf(__uint_as_float(v[j]) - m);
-                            const float d = xv[j] - g;
+                            const float d = xv - g;
                             S0 += e;
                             S1 = fmaf(e, d, S1);
                             S2 = fmaf(e * d, d, S2);
@@ -217,8 +218,13 @@ __global__ void __launch_bounds__(256, 1) asp_fused_kernel(const __grid_constant
                 }
                 tc_fence_before();
                 mbar_arrive(tempty(acc));
+                mbar_arrive(b_empty(stage));  // done reading the x tile of this stage
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1u;
+                if (++stage == AF_STAGES) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
             }
             const float inv = 1.f / S0;
             const float dm = S1 * inv;
@@ -240,16 +246,19 @@ __global__ void __launch_bounds__(256, 1) asp_fused_kernel(const __grid_constant
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 256);
+    if (warp == 2) tmem_dealloc(tmem_base, 128);
 }
 
 int asp_fused_build(AspFusedParams* p, const Planes& W, const Planes& att, const Planes& x, const Planes& gstat, const float* bn_scale,
                     const float* bn_shift, const Planes& out, float* out_raw, int B, int T, int P, int Tp, int C, int K, float eps) {
     PPV_REQUIRE(C % 128 == 0 && K % 64 == 0 && K <= 128, "asp_fused: C % 128 == 0 and K in {64,128} required");
     memset(p, 0, sizeof(*p));
+    PPV_REQUIRE(x.ld == C, "asp_fused: x row length must equal C");
     int rc = encode_planes_map(&p->mapW, W, 128);
     if (rc) return rc;
-    rc = encode_planes_map(&p->mapAtt, att, 128);
+    rc = encode_planes_map(&p->mapAtt, att, AF_NT);
+    if (rc) return rc;
+    rc = encode_planes_map_ex(&p->mapX, x, 128, AF_NT, false);
     if (rc) return rc;
     p->x = x;
     p->gstat = gstat;
@@ -269,8 +278,8 @@ int asp_fused_build(AspFusedParams* p, const Planes& W, const Planes& att, const
 
 int asp_fused_launch(const AspFusedParams& p, int precision, int num_sms, cudaStream_t st) {
     const bool x3 = precision == PPV_PREC_BF16X3;
-    const int ksteps = p.K / 64;
-    const int smem = 1024 + (1 + AF_STAGES) * ksteps * (x3 ? 2 : 1) * AF_TILE_BYTES + 128;
+    const int ksteps = p.K / 64, np = x3 ? 2 : 1;
+    const int smem = 1024 + ksteps * np * AF_A_TILE + AF_STAGES * (ksteps * np * AF_B_TILE + 2 * AF_X_TILE) + 128;
     static bool attr3 = false, attr1 = false;
     bool& attr = x3 ? attr3 : attr1;
     if (!attr) {

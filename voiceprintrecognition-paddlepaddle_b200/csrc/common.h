@@ -110,12 +110,14 @@ int gemm_build(GemmParams* gp, const GemmSource* srcs, int nsrc, const Planes& W
 int gemm_launch(const GemmParams& gp, int BN, int precision, int num_sms, cudaStream_t stream);
 int gemm_max_smem_setup();
 
-int encode_planes_map(CUtensorMap* m, const Planes& t, int box_rows);  // 3-D TMA map over split planes, box {64, box_rows, 1}
+int encode_planes_map(CUtensorMap* m, const Planes& t, int box_rows);  // 3-D TMA map over split planes, box {64, box_rows, 1}, SWIZZLE_128B
+int encode_planes_map_ex(CUtensorMap* m, const Planes& t, int box_cols, int box_rows, bool swizzle128);
 
 // ---- fused attentive statistics pooling (asp_fused.cu) ----------------------------------------------
 struct AspFusedParams {
     CUtensorMap mapW;    // planes [2][C][K]   box {64, 128, 1}
-    CUtensorMap mapAtt;  // planes [2][rows][K] box {64, 128, 1}
+    CUtensorMap mapAtt;  // planes [2][rows][K] box {64, 64, 1}
+    CUtensorMap mapX;    // planes [2][rows][C] box {128, 64, 1}, no swizzle
     Planes x;            // MFA output, padded time layout, ld = C
     Planes gstat;        // [B, 2C] (global mean | std): mean used as the shift
     const float* bn_scale;  // asp_bn folded, [2C]

@@ -315,22 +315,24 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// 3-D map over split planes [2][rows][ld] bf16, box = {64 cols, box_rows, 1 plane}, SWIZZLE_128B.
-int encode_planes_map(CUtensorMap* m, const Planes& t, int box_rows) {
+int encode_planes_map_ex(CUtensorMap* m, const Planes& t, int box_cols, int box_rows, bool swizzle128) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return fail(PPV_ECUDA, "cuTensorMapEncodeTiled entry point not available");
     if ((reinterpret_cast<uintptr_t>(t.base) & 15) || (t.ld % 8) || (t.plane_stride % 8))
         return fail(PPV_EINVAL, "planes tensor not 16-byte aligned");
     cuuint64_t dims[3] = {cuuint64_t(t.ld), cuuint64_t(t.rows), 2};
     cuuint64_t strides[2] = {cuuint64_t(t.ld) * 2, cuuint64_t(t.plane_stride) * 2};
-    cuuint32_t box[3] = {cuuint32_t(GEMM_BK), cuuint32_t(box_rows), 1};
+    cuuint32_t box[3] = {cuuint32_t(box_cols), cuuint32_t(box_rows), 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, t.base, dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, t.base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(PPV_ECUDA, "cuTensorMapEncodeTiled failed, CUresult " + std::to_string(int(r)));
     return PPV_OK;
 }
+
+// 3-D map over split planes [2][rows][ld] bf16, box = {64 cols, box_rows, 1 plane}, SWIZZLE_128B.
+int encode_planes_map(CUtensorMap* m, const Planes& t, int box_rows) { return encode_planes_map_ex(m, t, GEMM_BK, box_rows, true); }
 
 int gemm_build(GemmParams* gp, const GemmSource* srcs, int nsrc, const Planes& W, int M, int N, const Epilogue& epi,
                int BN) {
