@@ -31,7 +31,7 @@ constexpr int AF_X_TILE = AF_NT * 128 * 2;        // x tile       [64 fr x 128 c
 constexpr int AF_STAGES = 2;
 
 template <int NSPLIT>
-__global__ void __launch_bounds__(256, 1) asp_fused_kernel(const __grid_constant__ AspFusedParams p) {
+__global__ void __launch_bounds__(384, 1) asp_fused_kernel(const __grid_constant__ AspFusedParams p) {
     constexpr int NP = (NSPLIT == 3) ? 2 : 1;  // planes loaded per MMA operand
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -63,11 +63,11 @@ __global__ void __launch_bounds__(256, 1) asp_fused_kernel(const __grid_constant
         mbar_init(a_empty, 1);
         for (int s = 0; s < AF_STAGES; ++s) {
             mbar_init(b_full(s), 1);
-            mbar_init(b_empty(s), 1 + 128);  // MMA commit + the 128 epilogue threads that read the x tile
+            mbar_init(b_empty(s), 1 + 256);  // MMA commit + the 256 epilogue threads that read the x tile
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull(a), 1);
-            mbar_init(tempty(a), 128);
+            mbar_init(tempty(a), 256);
         }
         fence_mbar_init();
     }
@@ -166,8 +166,12 @@ __global__ void __launch_bounds__(256, 1) asp_fused_kernel(const __grid_constant
         }
     } else if (warp >= 4) {
         // ===================== epilogue: one thread = one channel =====================
+        // 8 warps: warps 4-7 take the first 32 frames of every 64-frame tile, warps 8-11 the second 32; the two
+        // partial (max, S0, S1, S2) of a channel are merged through shared memory at the end of the item.
         const int q = warp & 3;
+        const int half = (warp - 4) >> 2;
         const int cl = q * 32 + lane;  // channel within the slab == TMEM lane
+        float4* s_merge = reinterpret_cast<float4*>(smem_gen + (bar_base - smem_base) + 96);  // [128]
         int acc = 0, stage = 0;
         uint32_t acc_phase = 0, phase = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
@@ -183,36 +187,37 @@ __global__ void __launch_bounds__(256, 1) asp_fused_kernel(const __grid_constant
                 const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + acc * AF_NT;
                 const __nv_bfloat16* xs_hi = reinterpret_cast<const __nv_bfloat16*>(smem_gen + (s_base - smem_base) + stage * stage_bytes + b_bytes);
                 const __nv_bfloat16* xs_lo = xs_hi + AF_X_TILE / 2;
-#pragma unroll 1
-                for (int ch = 0; ch < AF_NT / 32; ++ch) {
+                {
+                    const int ch = half;
                     const int t0 = ft * AF_NT + ch * 32;
                     uint32_t v[32];
                     __syncwarp();
                     tmem_ld32(t_addr + ch * 32, v);
                     tmem_ld_wait();
                     const int nvalid = min(32, p.T - t0);  // warp-uniform
-                    if (nvalid <= 0) continue;
-                    float cm = -INFINITY;
+                    if (nvalid > 0) {
+                        float cm = -INFINITY;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < nvalid) cm = fmaxf(cm, __uint_as_float(v[j]));
-                    if (cm > m) {
-                        const float r = expf(m - cm);  // exp(-inf) = 0 on the first chunk
-                        S0 *= r;
-                        S1 *= r;
-                        S2 *= r;
-                        m = cm;
-                    }
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nvalid) cm = fmaxf(cm, __uint_as_float(v[j]));
+                        if (cm > m) {
+                            const float r = __expf(m - cm);  // exp(-inf) = 0 on the first chunk
+                            S0 *= r;
+                            S1 *= r;
+                            S2 *= r;
+                            m = cm;
+                        }
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (j < nvalid) {
-                            const int o = (ch * 32 + j) * 128 + cl;
-                            const float xv = __bfloat162float(xs_hi[o]) + __bfloat162float(xs_lo[o]);
-                            const float e = expf(__uint_as_float(v[j]) - m);
-                            const float d = xv - g;
-                            S0 += e;
-                            S1 = fmaf(e, d, S1);
-                            S2 = fmaf(e * d, d, S2);
+                        for (int j = 0; j < 32; ++j) {
+                            if (j < nvalid) {
+                                const int o = (ch * 32 + j) * 128 + cl;
+                                const float xv = __bfloat162float(xs_hi[o]) + __bfloat162float(xs_lo[o]);
+                                const float e = __expf(__uint_as_float(v[j]) - m);
+                                const float d = xv - g;
+                                S0 += e;
+                                S1 = fmaf(e, d, S1);
+                                S2 = fmaf(e * d, d, S2);
+                            }
                         }
                     }
                 }
@@ -226,6 +231,19 @@ __global__ void __launch_bounds__(256, 1) asp_fused_kernel(const __grid_constant
                     phase ^= 1u;
                 }
             }
+            // merge the two halves of the channel
+            if (half == 1) s_merge[cl] = make_float4(m, S0, S1, S2);
+            named_bar_sync(2, 256);
+            if (half == 0) {
+                const float4 o = s_merge[cl];
+                const float mm = fmaxf(m, o.x);
+                const float ra = __expf(m - mm), rb = (o.y > 0.f) ? __expf(o.x - mm) : 0.f;
+                S0 = S0 * ra + o.y * rb;
+                S1 = S1 * ra + o.z * rb;
+                S2 = S2 * ra + o.w * rb;
+            }
+            named_bar_sync(2, 256);  // s_merge may be overwritten by the next item
+            if (half == 1) continue;
             const float inv = 1.f / S0;
             const float dm = S1 * inv;
             const float mean = g + dm;
@@ -279,7 +297,7 @@ int asp_fused_build(AspFusedParams* p, const Planes& W, const Planes& att, const
 int asp_fused_launch(const AspFusedParams& p, int precision, int num_sms, cudaStream_t st) {
     const bool x3 = precision == PPV_PREC_BF16X3;
     const int ksteps = p.K / 64, np = x3 ? 2 : 1;
-    const int smem = 1024 + ksteps * np * AF_A_TILE + AF_STAGES * (ksteps * np * AF_B_TILE + 2 * AF_X_TILE) + 128;
+    const int smem = 1024 + ksteps * np * AF_A_TILE + AF_STAGES * (ksteps * np * AF_B_TILE + 2 * AF_X_TILE) + 96 + 128 * 16 + 64;
     static bool attr3 = false, attr1 = false;
     bool& attr = x3 ? attr3 : attr1;
     if (!attr) {
@@ -292,9 +310,9 @@ int asp_fused_launch(const AspFusedParams& p, int precision, int num_sms, cudaSt
     const int items = (p.C / 128) * p.B;
     const int grid = std::min(items, num_sms);
     if (x3)
-        asp_fused_kernel<3><<<grid, 256, smem, st>>>(p);
+        asp_fused_kernel<3><<<grid, 384, smem, st>>>(p);
     else
-        asp_fused_kernel<1><<<grid, 256, smem, st>>>(p);
+        asp_fused_kernel<1><<<grid, 384, smem, st>>>(p);
     PPV_LAUNCH_OK("asp_fused_kernel");
     return PPV_OK;
 }

@@ -183,25 +183,51 @@ int launch_colstats(const Planes& x, int col0, int C, int B, int T, int P, int T
 
 // ------------------------------------------------------------------------------------------------
 // out[r, oc0 + c] = scale[b(r), c] * z[r, c] + res[r, rc0 + c]   for every row of the padded layout.
+__device__ __forceinline__ void unpack8(const uint4& h, const uint4& l, float (&v)[8]) {
+    const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[i]));
+        const float2 lf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&lw[i]));
+        v[2 * i] = hf.x + lf.x;
+        v[2 * i + 1] = hf.y + lf.y;
+    }
+}
+// 8 channels (16 bytes per plane) per thread per iteration
 __global__ void __launch_bounds__(256)
     se_scale_res_kernel(Planes z, const float* __restrict__ scale, Planes res, int rc0, Planes out, int oc0, int C, int Tp,
                         int64_t rows) {
-    const int pairs = C >> 1;
-    const int64_t total = rows * pairs;
+    const int groups = C >> 3;
+    const int64_t total = rows * groups;
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-        const int64_t r = i / pairs;
-        const int c = int(i - r * pairs) * 2;
+        const int64_t r = i / groups;
+        const int c = int(i - r * groups) * 8;
         const int b = int(r / Tp);
-        const float2 zv = ld_split2(z.hi(), z.lo(), r * z.ld + c);
-        const float2 rv = ld_split2(res.hi(), res.lo(), r * res.ld + rc0 + c);
-        const float2 sv = *reinterpret_cast<const float2*>(scale + int64_t(b) * C + c);
-        st_split2(out.hi(), out.lo(), r * out.ld + oc0 + c, fmaf(sv.x, zv.x, rv.x), fmaf(sv.y, zv.y, rv.y));
+        float zv[8], rv[8];
+        unpack8(*reinterpret_cast<const uint4*>(z.hi() + r * z.ld + c), *reinterpret_cast<const uint4*>(z.lo() + r * z.ld + c), zv);
+        unpack8(*reinterpret_cast<const uint4*>(res.hi() + r * res.ld + rc0 + c),
+                *reinterpret_cast<const uint4*>(res.lo() + r * res.ld + rc0 + c), rv);
+        const float4 s0 = *reinterpret_cast<const float4*>(scale + int64_t(b) * C + c);
+        const float4 s1 = *reinterpret_cast<const float4*>(scale + int64_t(b) * C + c + 4);
+        const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(fmaf(sv[2 * k], zv[2 * k], rv[2 * k]), h0, l0);
+            split_bf16(fmaf(sv[2 * k + 1], zv[2 * k + 1], rv[2 * k + 1]), h1, l1);
+            h[k] = pack_bf16x2(h0, h1);
+            l[k] = pack_bf16x2(l0, l1);
+        }
+        *reinterpret_cast<uint4*>(out.hi() + r * out.ld + oc0 + c) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(out.lo() + r * out.ld + oc0 + c) = make_uint4(l[0], l[1], l[2], l[3]);
     }
 }
 
 int launch_se_scale_res(const Planes& z, const float* scale, const Planes& res, int rc0, const Planes& out, int oc0, int C,
                         int Tp, int64_t rows, int num_sms, cudaStream_t st) {
-    const int64_t total = rows * (C / 2);
+    PPV_REQUIRE(C % 8 == 0 && rc0 % 8 == 0 && oc0 % 8 == 0, "se_scale_res: 8-channel alignment required");
+    const int64_t total = rows * (C / 8);
     const int64_t want = (total + 255) / 256;
     const int grid = int(std::min<int64_t>(want, int64_t(num_sms) * 16));
     se_scale_res_kernel<<<grid, 256, 0, st>>>(z, scale, res, rc0, out, oc0, C, Tp, rows);

@@ -9,11 +9,11 @@
 // Operands are split-bf16 planes (hi, lo); PPV_PREC_BF16X3 issues hi*hi + lo*hi + hi*lo into one fp32
 // TMEM accumulator (fp32-grade), PPV_PREC_BF16 issues hi*hi only.
 //
-// Warp roles (256 threads, 1 CTA / SM, persistent over tiles):
+// Warp roles (384 threads, 1 CTA / SM, persistent over tiles):
 //   warp 0    TMA producer  : cp.async.bulk.tensor 3-D tiles (SWIZZLE_128B) into a STAGES-deep smem ring
 //   warp 1    MMA issuer    : one lane issues tcgen05.mma (M=128, N=BN, K=16) ; tcgen05.commit frees the slot
 //   warp 2    TMEM allocator
-//   warps 4-7 epilogue      : tcgen05.ld 32 columns at a time -> bias / ReLU / BN affine / tanh ->
+//   warps 4-11 epilogue     : (two warps per TMEM lane quarter, alternating 32-column chunks) tcgen05.ld 32 columns at a time -> bias / ReLU / BN affine / tanh ->
 //                             split-bf16 (or fp32) stores incl. the reflect-halo rows
 // TMEM holds two BN-column fp32 accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <stdio.h>
@@ -26,6 +26,9 @@
 #include "ptx.cuh"
 
 namespace ppv {
+
+constexpr int GEMM_EPI_THREADS = 256;                    // 8 epilogue warps: 2 per TMEM lane quarter
+constexpr int GEMM_THREADS = 128 + GEMM_EPI_THREADS;    // + TMA, MMA, TMEM-alloc, spare warps
 
 template <int BN, int NSPLIT>
 struct GemmCfg {
@@ -46,7 +49,7 @@ struct GemmCfg {
 };
 
 template <int BN, int NSPLIT>
-__global__ void __launch_bounds__(256, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams gp) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams gp) {
     using Cfg = GemmCfg<BN, NSPLIT>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -79,7 +82,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tcgen05_kernel(const __grid_const
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), 128);
+            mbar_init(tempty_bar(a), GEMM_EPI_THREADS);
         }
         fence_mbar_init();
     }
@@ -172,7 +175,8 @@ __global__ void __launch_bounds__(256, 1) gemm_tcgen05_kernel(const __grid_const
         // ===================== epilogue =====================
         const Epilogue& ep = gp.epi;
         const int q = warp & 3;             // TMEM lane quarter this warp may read
-        const int etid = threadIdx.x - 128;  // 0..127
+        const int etid = threadIdx.x - 128;  // 0..GEMM_EPI_THREADS-1
+        const int ehalf = (warp - 4) >> 2;   // two warps share a TMEM lane quarter and split the column chunks
         float* s_bias = s_vec;
         float* s_scale = s_vec + BN;
         float* s_shift = s_vec + 2 * BN;
@@ -182,15 +186,15 @@ __global__ void __launch_bounds__(256, 1) gemm_tcgen05_kernel(const __grid_const
             const int m0 = (tile / gp.n_tiles) * GEMM_BM;
             const int n0 = (tile % gp.n_tiles) * BN;
             // stage the per-column vectors of this N slice
-            named_bar_sync(1, 128);
-            for (int i = etid; i < BN; i += 128) {
+            named_bar_sync(1, GEMM_EPI_THREADS);
+            for (int i = etid; i < BN; i += GEMM_EPI_THREADS) {
                 const int n = n0 + i;
                 const bool ok = n < gp.N;
                 s_bias[i] = (ep.bias && ok) ? __ldg(ep.bias + n) : 0.f;
                 s_scale[i] = (ep.bn_scale && ok) ? __ldg(ep.bn_scale + n) : 1.f;
                 s_shift[i] = (ep.bn_shift && ok) ? __ldg(ep.bn_shift + n) : 0.f;
             }
-            named_bar_sync(1, 128);
+            named_bar_sync(1, GEMM_EPI_THREADS);
 
             // row bookkeeping
             const int64_t row = int64_t(m0) + q * 32 + lane;
@@ -212,7 +216,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tcgen05_kernel(const __grid_const
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = ehalf; c < BN / 32; c += GEMM_EPI_THREADS / 128) {
                 uint32_t v[32];
                 __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the divergent stores
                 tmem_ld32(t_addr + c * 32, v);
@@ -398,7 +402,7 @@ static int launch_one(const GemmParams& gp, int num_sms, cudaStream_t stream) {
     }
     const int tiles = gp.m_tiles * gp.n_tiles;
     const int grid = std::min(tiles, num_sms);
-    gemm_tcgen05_kernel<BN, NSPLIT><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(gp);
+    gemm_tcgen05_kernel<BN, NSPLIT><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(gp);
     PPV_LAUNCH_OK("gemm_tcgen05_kernel");
     return PPV_OK;
 }
