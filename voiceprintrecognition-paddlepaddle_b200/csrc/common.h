@@ -113,6 +113,18 @@ int gemm_max_smem_setup();
 int encode_planes_map(CUtensorMap* m, const Planes& t, int box_rows);  // 3-D TMA map over split planes, box {64, box_rows, 1}, SWIZZLE_128B
 int encode_planes_map_ex(CUtensorMap* m, const Planes& t, int box_cols, int box_rows, bool swizzle128);
 
+// ---- Res2Net dilated conv, weight-stationary, one tall activation tile per source (res2conv.cu) ------
+struct Res2Params {
+    CUtensorMap mapA[2];  // source planes, box {64, 128 + 8, 1}
+    CUtensorMap mapW;     // weight planes [2][64][nsrc*3*64], box {64, 64, 1}
+    int a_col[2];
+    int nsrc, dil;
+    int M, m_tiles;
+    Epilogue epi;
+};
+int res2conv_build(Res2Params* rp, const GemmSource* srcs, int nsrc, const Planes& W, int M, int dil, const Epilogue& epi);
+int res2conv_launch(const Res2Params& rp, int precision, int num_sms, cudaStream_t st);
+
 // ---- fused attentive statistics pooling (asp_fused.cu) ----------------------------------------------
 struct AspFusedParams {
     CUtensorMap mapW;    // planes [2][C][K]   box {64, 128, 1}

@@ -12,6 +12,8 @@
 //   * ASP's tiled [mean;std] concat (K = 4608) becomes a per-utterance bias: W[:, C:3C] . [mean;std]
 //     is one tiny GEMM, so the attention TDNN runs with K = 1536 (2.857 GFLOP / utterance executed
 //     instead of 3.090).
+#include <stdlib.h>
+
 #include <map>
 #include <string>
 #include <vector>
@@ -44,9 +46,10 @@ struct KSpec {  // one K group: `ncols` columns of a source at a row offset <- w
 enum Buf { B_FEAT, B_X0, B_H, B_Y, B_Z, B_CAT, B_MFA, B_ATT, B_GSTAT, B_POOL, B_SEM, B_SEH, B_COUNT };
 
 struct Step {
-    enum Kind { GEMM, SE_SQUEEZE, SE_SCALE, ASP_GLOBAL, ASP_FUSED } kind;
+    enum Kind { GEMM, RES2, SE_SQUEEZE, SE_SCALE, ASP_GLOBAL, ASP_FUSED } kind;
     GemmParams gp;
     AspFusedParams ap;
+    Res2Params rp;
     int BN = 0;
     int blk = 0;  // block index for the SE steps
 };
@@ -398,6 +401,8 @@ static int build_plan(EcapaModel* m, int B, int T, void* ws, size_t ws_bytes, cu
     m->steps.clear();
     const int Tp = m->Tp, P = m->P, C = m->C, C3 = m->C3, w = m->width;
     const int64_t R = int64_t(B) * Tp;
+    const char* r2env = getenv("PPV_RES2_GEMM");  // debugging aid: 1 = run the Res2Net convs through the generic gather-GEMM
+    const bool use_res2_kernel = (w == 64) && !(r2env && r2env[0] == '1');
 
     auto add_gemm = [&](const ConvW& cw, const std::vector<KSpec>& ks, const Planes* src_override, int override_col0, int M,
                         Epilogue ep) -> int {
@@ -450,8 +455,24 @@ static int build_plan(EcapaModel* m, int B, int T, void* ws, size_t ws_bytes, cu
         rc = add_gemm(m->tdnn1[b - 1], {{-1, 0, C, 0, 0, C, 0}}, &X, xcol, int(R), planes_out(m->bufs[B_H], 0, true));
         if (rc) return rc;
         for (int j = 1; j < m->scale; ++j) {
-            rc = add_gemm(m->res2[b - 1][j], spec_res2(m, b, j), nullptr, 0, int(R), planes_out(m->bufs[B_Y], j * w, true));
-            if (rc) return rc;
+            if (use_res2_kernel) {  // weight-stationary kernel, one tall tile per source (res2conv.cu)
+                GemmSource srcs[2];
+                srcs[0] = GemmSource{m->bufs[B_H], j * w, w, 0};
+                srcs[1] = GemmSource{m->bufs[B_Y], (j - 1) * w, w, 0};
+                Epilogue ep = planes_out(m->bufs[B_Y], j * w, true);
+                const ConvW& cw = m->res2[b - 1][j];
+                ep.bias = cw.bias;
+                ep.bn_scale = cw.bn_scale;
+                ep.bn_shift = cw.bn_shift;
+                Step stp;
+                stp.kind = Step::RES2;
+                rc = res2conv_build(&stp.rp, srcs, j >= 2 ? 2 : 1, cw.W, int(R), m->cfg.dilations[b], ep);
+                if (rc) return rc;
+                m->steps.push_back(stp);
+            } else {
+                rc = add_gemm(m->res2[b - 1][j], spec_res2(m, b, j), nullptr, 0, int(R), planes_out(m->bufs[B_Y], j * w, true));
+                if (rc) return rc;
+            }
         }
         rc = add_gemm(m->tdnn2[b - 1], {{B_H, 0, w, 0, 0, w, 0}, {B_Y, w, C - w, 0, w, C - w, 0}}, nullptr, 0, int(R),
                       planes_out(m->bufs[B_Z], 0, false));
@@ -577,11 +598,12 @@ int ecapa_forward(EcapaModel* m, const float* feat, Fbank* fb, const float* wav,
     prof_mark(1, false);
     if (rc) return rc;
     for (const Step& s : m->steps) {
-        const bool tensor_step = (s.kind == Step::GEMM || s.kind == Step::ASP_FUSED);
+        const bool tensor_step = (s.kind == Step::GEMM || s.kind == Step::ASP_FUSED || s.kind == Step::RES2);
         prof_mark(tensor_step ? 0 : 1, true);
         if (tensor_step) m->launches_gemm += 1; else m->launches_other += 1;
         switch (s.kind) {
             case Step::GEMM: rc = gemm_launch(s.gp, s.BN, m->precision, m->num_sms, st); break;
+            case Step::RES2: rc = res2conv_launch(s.rp, m->precision, m->num_sms, st); break;
             case Step::SE_SQUEEZE:
                 rc = launch_colstats(m->bufs[B_Z], 0, C, B, T, P, Tp, 0, 0.f, nullptr, m->bufs[B_SEM], st);
                 break;

@@ -23,12 +23,10 @@
 #include <mutex>
 
 #include "common.h"
+#include "gemm_epilogue.cuh"
 #include "ptx.cuh"
 
 namespace ppv {
-
-constexpr int GEMM_EPI_THREADS = 256;                    // 8 epilogue warps: 2 per TMEM lane quarter
-constexpr int GEMM_THREADS = 128 + GEMM_EPI_THREADS;    // + TMA, MMA, TMEM-alloc, spare warps
 
 template <int BN, int NSPLIT>
 struct GemmCfg {
@@ -173,124 +171,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        const Epilogue& ep = gp.epi;
-        const int q = warp & 3;             // TMEM lane quarter this warp may read
+        const int q = warp & 3;              // TMEM lane quarter this warp may read
         const int etid = threadIdx.x - 128;  // 0..GEMM_EPI_THREADS-1
         const int ehalf = (warp - 4) >> 2;   // two warps share a TMEM lane quarter and split the column chunks
-        float* s_bias = s_vec;
-        float* s_scale = s_vec + BN;
-        float* s_shift = s_vec + 2 * BN;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m0 = (tile / gp.n_tiles) * GEMM_BM;
             const int n0 = (tile % gp.n_tiles) * BN;
-            // stage the per-column vectors of this N slice
-            named_bar_sync(1, GEMM_EPI_THREADS);
-            for (int i = etid; i < BN; i += GEMM_EPI_THREADS) {
-                const int n = n0 + i;
-                const bool ok = n < gp.N;
-                s_bias[i] = (ep.bias && ok) ? __ldg(ep.bias + n) : 0.f;
-                s_scale[i] = (ep.bn_scale && ok) ? __ldg(ep.bn_scale + n) : 1.f;
-                s_shift[i] = (ep.bn_shift && ok) ? __ldg(ep.bn_shift + n) : 0.f;
-            }
-            named_bar_sync(1, GEMM_EPI_THREADS);
-
-            // row bookkeeping
-            const int64_t row = int64_t(m0) + q * 32 + lane;
-            bool valid = row < gp.M;
-            int64_t mirror_a = -1, mirror_b = -1;
-            int64_t grp = 0;
-            if (ep.Tp > 0) {
-                grp = row / ep.Tp;
-                const int t = int(row - grp * ep.Tp) - ep.P;
-                valid = valid && t >= 0 && t < ep.T;
-                if (ep.halo && valid) {
-                    if (t >= 1 && t <= ep.P) mirror_a = row - 2 * t;
-                    const int u = ep.T - 1 - t;  // distance from the last frame
-                    if (u >= 1 && u <= ep.P) mirror_b = row + 2 * u;
-                }
-            }
-
-            mbar_wait(tfull_bar(acc), acc_phase);
-            tc_fence_after();
-            const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
-#pragma unroll 1
-            for (int c = ehalf; c < BN / 32; c += GEMM_EPI_THREADS / 128) {
-                uint32_t v[32];
-                __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the divergent stores
-                tmem_ld32(t_addr + c * 32, v);
-                tmem_ld_wait();
-                const int col = n0 + c * 32;
-                if (!valid || col >= gp.N) continue;
-                float x[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + s_bias[c * 32 + j];
-                if (ep.rowgrp_bias) {
-                    const float4* rg = reinterpret_cast<const float4*>(ep.rowgrp_bias + grp * gp.N + col);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 b4 = __ldg(rg + j);
-                        x[4 * j + 0] += b4.x;
-                        x[4 * j + 1] += b4.y;
-                        x[4 * j + 2] += b4.z;
-                        x[4 * j + 3] += b4.w;
-                    }
-                }
-                if (ep.relu) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
-                }
-                if (ep.bn_scale) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) x[j] = fmaf(x[j], s_scale[c * 32 + j], s_shift[c * 32 + j]);
-                }
-                if (ep.tanh_) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) x[j] = tanhf(x[j]);
-                }
-                if (ep.sigmoid_) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) x[j] = 1.f / (1.f + expf(-x[j]));
-                }
-                if (ep.out_mode == OUT_F32) {
-                    float* dstf = static_cast<float*>(ep.out) + row * ep.out_ld + ep.out_col0 + col;
-                    if (ep.f32_vec_ok && col + 32 <= gp.N) {
-                        float4* dst = reinterpret_cast<float4*>(dstf);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) dst[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-                    } else {  // ragged N (cosine scoring): guarded scalar stores
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (col + j < gp.N) dstf[j] = x[j];
-                    }
-                } else {
-                    uint32_t h[16], l[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        __nv_bfloat16 h0, l0, h1, l1;
-                        split_bf16(x[2 * j], h0, l0);
-                        split_bf16(x[2 * j + 1], h1, l1);
-                        h[j] = pack_bf16x2(h0, h1);
-                        l[j] = pack_bf16x2(l0, l1);
-                    }
-                    __nv_bfloat16* obase = static_cast<__nv_bfloat16*>(ep.out) + ep.out_col0 + col;
-                    auto store_row = [&](int64_t r) {
-                        uint4* ph = reinterpret_cast<uint4*>(obase + r * ep.out_ld);
-                        uint4* pl = reinterpret_cast<uint4*>(obase + ep.out_plane_stride + r * ep.out_ld);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            ph[j] = make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
-                            pl[j] = make_uint4(l[4 * j], l[4 * j + 1], l[4 * j + 2], l[4 * j + 3]);
-                        }
-                    };
-                    store_row(row);
-                    if (mirror_a >= 0) store_row(mirror_a);
-                    if (mirror_b >= 0) store_row(mirror_b);
-                }
-            }
-            tc_fence_before();
-            mbar_arrive(tempty_bar(acc));
+            epilogue_tile<BN>(gp.epi, gp.M, gp.N, m0, n0, tmem_base + acc * BN, tfull_bar(acc), acc_phase, tempty_bar(acc), q, lane, ehalf,
+                              etid, s_vec);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
         }
