@@ -7,8 +7,9 @@
 //     shared memory for all of the CTA's tiles (weight-stationary);
 //   * per source (x_j, y_{j-1}) ONE tall activation tile of 128 + 2*4 rows is loaded per output tile; the three
 //     conv taps are the SAME shared-memory tile read at row offsets 4-d, 4, 4+d: the UMMA descriptor's start
-//     address moves by whole 128-byte rows and its base_offset field carries (row mod 8) so the 128B-swizzle phase
-//     still matches what TMA wrote.
+//     address simply moves by whole 128-byte rows.  Measured on B200: the SWIZZLE_128B XOR phase is a function of the
+//     absolute shared-memory address (bits [7,10)), exactly as TMA wrote it, so any row of a 1024-byte-aligned slot is a
+//     valid matrix start with base_offset = 0 (setting base_offset = row mod 8 gives WRONG results).
 // L2 -> SM traffic per 128-row tile: 2 x 2 x 17 KB = 70 KB instead of 288 KB.
 #include <stdio.h>
 #include <string.h>
@@ -37,8 +38,10 @@ struct R2Cfg {
 
 // descriptor for rows [roff, roff+128) of a tall SWIZZLE_128B tile whose slot is 1024-byte aligned
 __device__ __forceinline__ uint64_t tall_tile_desc(uint32_t slot_addr, int roff) {
+    // The 128B-swizzle XOR is a function of the absolute shared-memory address bits [7,10) (as TMA wrote it), so a
+    // row-shifted start address needs no base_offset as long as the slot itself is 1024-byte aligned.
     const uint32_t addr = slot_addr + uint32_t(roff) * 128u;
-    return make_sw128_kmajor_desc(addr) | (uint64_t((addr >> 7) & 7u) << 49);
+    return make_sw128_kmajor_desc(addr);
 }
 
 template <int NSPLIT>
