@@ -147,12 +147,13 @@ int ppv_aam_backward(const float* emb, const float* W, const int64_t* labels, co
 /* ---------------------------------------------------------------------------------------------
  * Test hook for the tensor-core GEMM (not a reference entry point): out[M,N] = A[M,K] * W[N,K]^T
  * (+bias, ReLU, BN affine as flagged) through the same tcgen05/TMA kernel the model uses.
- * A, W, out fp32 device; ws >= ppv_gemm_test_workspace_bytes.
+ * A, W, out fp32 device; ws >= ppv_gemm_test_workspace_bytes.  block_n in {64,128,256}; block_k in {64,32}
+ * (K elements per pipeline stage: SWIZZLE_128B / SWIZZLE_64B tiles).
  * ------------------------------------------------------------------------------------------- */
 size_t ppv_gemm_test_workspace_bytes(int M, int N, int K);
 int ppv_gemm_test(const float* A, const float* W, const float* bias, const float* bn_scale, const float* bn_shift,
-                  int relu, int M, int N, int K, int block_n, int precision, float* out, void* ws, size_t ws_bytes,
-                  void* stream);
+                  int relu, int M, int N, int K, int block_n, int block_k, int precision, float* out, void* ws,
+                  size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -9,7 +9,7 @@ from ppvector import _lib
 pytestmark = pytest.mark.gpu
 
 
-def run_gemm(A, W, bias=None, scale=None, shift=None, relu=0, bn=128, prec=_lib.PPV_PREC_BF16X3):
+def run_gemm(A, W, bias=None, scale=None, shift=None, relu=0, bn=128, prec=_lib.PPV_PREC_BF16X3, bk=64):
     lib = _lib.load()
     M, K = A.shape
     N = W.shape[0]
@@ -17,7 +17,7 @@ def run_gemm(A, W, bias=None, scale=None, shift=None, relu=0, bn=128, prec=_lib.
     nbytes = lib.ppv_gemm_test_workspace_bytes(M, N, K)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=A.device)
     _lib.check(lib.ppv_gemm_test(_lib.ptr(A), _lib.ptr(W), _lib.ptr(bias), _lib.ptr(scale), _lib.ptr(shift), relu, M, N, K,
-                                 bn, prec, _lib.ptr(out), C.c_void_p(ws.data_ptr()), nbytes, _lib.current_stream()),
+                                 bn, bk, prec, _lib.ptr(out), C.c_void_p(ws.data_ptr()), nbytes, _lib.current_stream()),
                "ppv_gemm_test")
     torch.cuda.synchronize()
     return out
@@ -47,6 +47,24 @@ def test_gemm_x3_matches_fp64(cuda, M, N, K, bn):
     scale_ = ref.abs().max().item()
     assert torch.isfinite(out).all()
     assert err < 2e-5 * max(scale_, 1.0), (err, scale_)
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(128, 256, 32, 256), (300, 512, 512, 256), (1000, 128, 192, 128), (4096, 1536, 1536, 256)])
+@pytest.mark.parametrize("prec", [_lib.PPV_PREC_BF16X3, _lib.PPV_PREC_BF16])
+def test_gemm_bk32_swizzle64(cuda, M, N, K, bn, prec):
+    """32-wide k-steps: SWIZZLE_64B tiles, twice the ring slots"""
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(cuda)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(cuda)
+    if K % 64:
+        pytest.skip("the test hook pads K to 64")
+    out = run_gemm(A, W, bn=bn, prec=prec, bk=32)
+    if prec == _lib.PPV_PREC_BF16:
+        ref = ref_gemm(A.bfloat16().float(), W.bfloat16().float())
+        assert (out.double() - ref).abs().max().item() < 1e-4
+    else:
+        ref = ref_gemm(A, W)
+        assert (out.double() - ref).abs().max().item() < 2e-5 * max(ref.abs().max().item(), 1.0)
 
 
 @pytest.mark.parametrize("bn", [64, 128, 256])

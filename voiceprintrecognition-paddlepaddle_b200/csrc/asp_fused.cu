@@ -276,7 +276,7 @@ int asp_fused_build(AspFusedParams* p, const Planes& W, const Planes& att, const
     if (rc) return rc;
     rc = encode_planes_map(&p->mapAtt, att, AF_NT);
     if (rc) return rc;
-    rc = encode_planes_map_ex(&p->mapX, x, 128, AF_NT, false);
+    rc = encode_planes_map_ex(&p->mapX, x, 128, AF_NT, 0);
     if (rc) return rc;
     p->x = x;
     p->gstat = gstat;

@@ -241,7 +241,7 @@ size_t ppv_gemm_test_workspace_bytes(int M, int N, int K) {
     return au(au(size_t(M), 128) * Kp * 4, 256) + au(au(size_t(N), 256) * Kp * 4, 256) + 256;
 }
 int ppv_gemm_test(const float* A, const float* W, const float* bias, const float* bn_scale, const float* bn_shift, int relu, int M,
-                  int N, int K, int block_n, int precision, float* out, void* ws, size_t ws_bytes, void* stream) {
+                  int N, int K, int block_n, int block_k, int precision, float* out, void* ws, size_t ws_bytes, void* stream) {
     PPV_GUARD_BEGIN
     PPV_REQUIRE(A && W && out && ws, "ppv_gemm_test: null argument");
     PPV_REQUIRE(ws_bytes >= ppv_gemm_test_workspace_bytes(M, N, K), "ppv_gemm_test: workspace too small");
@@ -273,7 +273,7 @@ int ppv_gemm_test(const float* A, const float* W, const float* bias, const float
     ep.out = out;
     ep.out_ld = N;
     GemmParams gp;
-    rc = gemm_build(&gp, &src, 1, pw, M, N, ep, block_n);
+    rc = gemm_build(&gp, &src, 1, pw, M, N, ep, block_n, block_k);
     if (rc) return rc;
     return gemm_launch(gp, block_n, precision, device_sm_count(), st);
     PPV_GUARD_END

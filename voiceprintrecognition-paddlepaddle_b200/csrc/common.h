@@ -90,6 +90,7 @@ struct GemmParams {
     CUtensorMap mapB;
     KStep ksteps[GEMM_MAX_KSTEPS];
     int num_ksteps;
+    int bk;  // K elements per k-step (64 or 32)
     int M, N;
     int m_tiles, n_tiles;
     Epilogue epi;
@@ -106,12 +107,12 @@ struct GemmSource {
 //   PPV_PREC_BF16X3: A_hi*B_hi + A_lo*B_hi + A_hi*B_lo  (fp32-grade, ~2^-16 relative per product)
 //   PPV_PREC_BF16  : A_hi*B_hi only
 int gemm_build(GemmParams* gp, const GemmSource* srcs, int nsrc, const Planes& W, int M, int N, const Epilogue& epi,
-               int BN);
+               int BN, int BK = GEMM_BK);
 int gemm_launch(const GemmParams& gp, int BN, int precision, int num_sms, cudaStream_t stream);
 int gemm_max_smem_setup();
 
 int encode_planes_map(CUtensorMap* m, const Planes& t, int box_rows);  // 3-D TMA map over split planes, box {64, box_rows, 1}, SWIZZLE_128B
-int encode_planes_map_ex(CUtensorMap* m, const Planes& t, int box_cols, int box_rows, bool swizzle128);
+int encode_planes_map_ex(CUtensorMap* m, const Planes& t, int box_cols, int box_rows, int swizzle_bytes);  // 0 / 64 / 128
 
 // ---- Res2Net dilated conv, weight-stationary, one tall activation tile per source (res2conv.cu) ------
 struct Res2Params {

@@ -28,27 +28,44 @@
 
 namespace ppv {
 
-template <int BN, int NSPLIT>
+// BK = K elements per pipeline stage: 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B).  The smaller
+// stage keeps the same bytes per MMA but doubles the number of ring slots, i.e. more TMA bytes in flight for the same
+// shared memory: the K=512 layers are bound by load latency x bytes-in-flight, not by the tensor pipe.
+template <int BN, int NSPLIT, int BK>
 struct GemmCfg {
     static constexpr int NA = (NSPLIT == 3) ? 2 : 1;  // A tiles per stage (hi[, lo])
     static constexpr int NB = NA;
-    static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
-    static constexpr int B_BYTES = BN * GEMM_BK * 2;
+    static constexpr int A_BYTES = GEMM_BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = NA * A_BYTES + NB * B_BYTES;
     static constexpr int VEC_BYTES = 3 * BN * 4;  // bias / bn_scale / bn_shift slices
     static constexpr int BAR_BYTES = 256;
     static constexpr int MAX_SMEM = 232448;  // 227 KB
     static constexpr int STAGES_RAW = (MAX_SMEM - 1024 - VEC_BYTES - BAR_BYTES) / STAGE_BYTES;
-    static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + VEC_BYTES + BAR_BYTES;
     static constexpr int TMEM_COLS = 2 * BN;  // 128 / 256 / 512: power of two >= 32
     static_assert(STAGES >= 2, "need at least a double buffer");
     static_assert(BN == 64 || BN == 128 || BN == 256, "BN");
+    static_assert(BK == 64 || BK == 32, "BK");
 };
 
-template <int BN, int NSPLIT>
+template <int BK>
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
+    if (BK == 64) return make_sw128_kmajor_desc(smem_addr);
+    // SWIZZLE_64B: rows of 32 bf16 (64 B), 8-row groups 512 B apart, layout type 4
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3fff);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(512 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(4) << 61;
+    return d;
+}
+
+template <int BN, int NSPLIT, int BK>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams gp) {
-    using Cfg = GemmCfg<BN, NSPLIT>;
+    using Cfg = GemmCfg<BN, NSPLIT, BK>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment.
@@ -117,7 +134,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                         tma_load_3d(sa + p * Cfg::A_BYTES, ma, fb, ks.a_col, m0 + ks.row_off, p);
 #pragma unroll
                     for (int p = 0; p < Cfg::NB; ++p)
-                        tma_load_3d(sb + p * Cfg::B_BYTES, &gp.mapB, fb, s * GEMM_BK, n0, p);
+                        tma_load_3d(sb + p * Cfg::B_BYTES, &gp.mapB, fb, s * BK, n0, p);
                 }
                 __syncwarp();
                 if (++stage == STAGES) {
@@ -143,19 +160,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                 if (lane == 0) {
                     const uint32_t sa = tiles_base + stage * Cfg::STAGE_BYTES;
                     const uint32_t sb = sa + Cfg::NA * Cfg::A_BYTES;
-                    const uint64_t a_hi = make_sw128_kmajor_desc(sa);
-                    const uint64_t b_hi = make_sw128_kmajor_desc(sb);
+                    const uint64_t a_hi = make_kmajor_desc<BK>(sa);
+                    const uint64_t b_hi = make_kmajor_desc<BK>(sb);
                     // K advance inside the 128-byte swizzle atom: +32 B (16 bf16) per UMMA_K => +2 in desc.lo
 #pragma unroll
-                    for (int k = 0; k < GEMM_BK / 16; ++k)
+                    for (int k = 0; k < BK / 16; ++k)
                         umma_bf16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (s > 0 || k > 0) ? 1u : 0u);
                     if (NSPLIT == 3) {
-                        const uint64_t a_lo = make_sw128_kmajor_desc(sa + Cfg::A_BYTES);
-                        const uint64_t b_lo = make_sw128_kmajor_desc(sb + Cfg::B_BYTES);
+                        const uint64_t a_lo = make_kmajor_desc<BK>(sa + Cfg::A_BYTES);
+                        const uint64_t b_lo = make_kmajor_desc<BK>(sb + Cfg::B_BYTES);
 #pragma unroll
-                        for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+                        for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
 #pragma unroll
-                        for (int k = 0; k < GEMM_BK / 16; ++k) umma_bf16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+                        for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
                     }
                     umma_commit(empty_bar(stage));                   // smem slot free when these MMAs retire
                     if (s == nk - 1) umma_commit(tfull_bar(acc));   // accumulator complete
@@ -209,7 +226,7 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-int encode_planes_map_ex(CUtensorMap* m, const Planes& t, int box_cols, int box_rows, bool swizzle128) {
+int encode_planes_map_ex(CUtensorMap* m, const Planes& t, int box_cols, int box_rows, int swizzle_bytes) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return fail(PPV_ECUDA, "cuTensorMapEncodeTiled entry point not available");
     if ((reinterpret_cast<uintptr_t>(t.base) & 15) || (t.ld % 8) || (t.plane_stride % 8))
@@ -219,17 +236,19 @@ int encode_planes_map_ex(CUtensorMap* m, const Planes& t, int box_cols, int box_
     cuuint32_t box[3] = {cuuint32_t(box_cols), cuuint32_t(box_rows), 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, t.base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(PPV_ECUDA, "cuTensorMapEncodeTiled failed, CUresult " + std::to_string(int(r)));
     return PPV_OK;
 }
 
 // 3-D map over split planes [2][rows][ld] bf16, box = {64 cols, box_rows, 1 plane}, SWIZZLE_128B.
-int encode_planes_map(CUtensorMap* m, const Planes& t, int box_rows) { return encode_planes_map_ex(m, t, GEMM_BK, box_rows, true); }
+int encode_planes_map(CUtensorMap* m, const Planes& t, int box_rows) { return encode_planes_map_ex(m, t, GEMM_BK, box_rows, 128); }
 
 int gemm_build(GemmParams* gp, const GemmSource* srcs, int nsrc, const Planes& W, int M, int N, const Epilogue& epi,
-               int BN) {
+               int BN, int BK) {
+    PPV_REQUIRE(BK == 64 || BK == 32, "gemm_build: BK must be 64 or 32");
     PPV_REQUIRE(BN == 64 || BN == 128 || BN == 256, "gemm_build: BN must be 64/128/256");
     PPV_REQUIRE(epi.out_mode == OUT_F32 || N % 32 == 0, "gemm_build: planes output needs N % 32 == 0");
     PPV_REQUIRE(!epi.rowgrp_bias || N % 32 == 0, "gemm_build: row-group bias needs N % 32 == 0");
@@ -240,7 +259,7 @@ int gemm_build(GemmParams* gp, const GemmSource* srcs, int nsrc, const Planes& W
     int ks = 0;
     for (int i = 0; i < nsrc; ++i) {
         const GemmSource& s = srcs[i];
-        PPV_REQUIRE(s.ncols % GEMM_BK == 0 && s.col0 % 8 == 0, "gemm_build: source K slice must be a multiple of 64");
+        PPV_REQUIRE(s.ncols % 64 == 0 && s.col0 % 8 == 0, "gemm_build: source K slice must be a multiple of 64");
         PPV_REQUIRE(s.col0 + s.ncols <= s.t.ld, "gemm_build: source K slice exceeds the row");
         int mi = -1;
         for (int j = 0; j < nmaps; ++j)
@@ -249,10 +268,10 @@ int gemm_build(GemmParams* gp, const GemmSource* srcs, int nsrc, const Planes& W
             PPV_REQUIRE(nmaps < GEMM_MAX_MAPS, "gemm_build: too many distinct A tensors");
             mi = nmaps++;
             bases[mi] = s.t.base;
-            int rc = encode_planes_map(&gp->mapA[mi], s.t, GEMM_BM);
+            int rc = encode_planes_map_ex(&gp->mapA[mi], s.t, BK, GEMM_BM, BK * 2);
             if (rc) return rc;
         }
-        for (int c = 0; c < s.ncols; c += GEMM_BK) {
+        for (int c = 0; c < s.ncols; c += BK) {
             PPV_REQUIRE(ks < GEMM_MAX_KSTEPS, "gemm_build: too many k-steps");
             gp->ksteps[ks].map = int16_t(mi);
             gp->ksteps[ks].row_off = int16_t(s.row_off);
@@ -262,11 +281,12 @@ int gemm_build(GemmParams* gp, const GemmSource* srcs, int nsrc, const Planes& W
     }
     for (int j = nmaps; j < GEMM_MAX_MAPS; ++j) gp->mapA[j] = gp->mapA[0];
     PPV_REQUIRE(ks > 0, "gemm_build: empty K");
-    PPV_REQUIRE(W.ld == ks * GEMM_BK, "gemm_build: weight K does not match the k-steps");
+    PPV_REQUIRE(W.ld == ks * BK, "gemm_build: weight K does not match the k-steps");
     PPV_REQUIRE(W.rows >= N, "gemm_build: weight rows < N");
-    int rc = encode_planes_map(&gp->mapB, W, BN);
+    int rc = encode_planes_map_ex(&gp->mapB, W, BK, BN, BK * 2);
     if (rc) return rc;
     gp->num_ksteps = ks;
+    gp->bk = BK;
     gp->M = M;
     gp->N = N;
     gp->m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
@@ -281,28 +301,34 @@ int gemm_build(GemmParams* gp, const GemmSource* srcs, int nsrc, const Planes& W
     return PPV_OK;
 }
 
-template <int BN, int NSPLIT>
+template <int BN, int NSPLIT, int BK>
 static int launch_one(const GemmParams& gp, int num_sms, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN, NSPLIT>;
+    using Cfg = GemmCfg<BN, NSPLIT, BK>;
     static bool attr_set = false;
     if (!attr_set) {
-        PPV_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        PPV_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, NSPLIT, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES));
         attr_set = true;
     }
     const int tiles = gp.m_tiles * gp.n_tiles;
     const int grid = std::min(tiles, num_sms);
-    gemm_tcgen05_kernel<BN, NSPLIT><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(gp);
+    gemm_tcgen05_kernel<BN, NSPLIT, BK><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(gp);
     PPV_LAUNCH_OK("gemm_tcgen05_kernel");
     return PPV_OK;
+}
+
+template <int BN>
+static int launch_bn(const GemmParams& gp, bool x3, int num_sms, cudaStream_t stream) {
+    if (gp.bk == 32) return x3 ? launch_one<BN, 3, 32>(gp, num_sms, stream) : launch_one<BN, 1, 32>(gp, num_sms, stream);
+    return x3 ? launch_one<BN, 3, 64>(gp, num_sms, stream) : launch_one<BN, 1, 64>(gp, num_sms, stream);
 }
 
 int gemm_launch(const GemmParams& gp, int BN, int precision, int num_sms, cudaStream_t stream) {
     const bool x3 = (precision == PPV_PREC_BF16X3);
     switch (BN) {
-        case 64: return x3 ? launch_one<64, 3>(gp, num_sms, stream) : launch_one<64, 1>(gp, num_sms, stream);
-        case 128: return x3 ? launch_one<128, 3>(gp, num_sms, stream) : launch_one<128, 1>(gp, num_sms, stream);
-        case 256: return x3 ? launch_one<256, 3>(gp, num_sms, stream) : launch_one<256, 1>(gp, num_sms, stream);
+        case 64: return launch_bn<64>(gp, x3, num_sms, stream);
+        case 128: return launch_bn<128>(gp, x3, num_sms, stream);
+        case 256: return launch_bn<256>(gp, x3, num_sms, stream);
     }
     return fail(PPV_EINVAL, "gemm_launch: bad BN");
 }

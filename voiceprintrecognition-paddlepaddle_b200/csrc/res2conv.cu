@@ -191,7 +191,7 @@ int res2conv_build(Res2Params* rp, const GemmSource* srcs, int nsrc, const Plane
     memset(static_cast<void*>(rp), 0, sizeof(*rp));
     for (int s = 0; s < nsrc; ++s) {
         PPV_REQUIRE(srcs[s].ncols == 64 && srcs[s].col0 % 8 == 0, "res2conv: each source is one 64-channel chunk");
-        int rc = encode_planes_map_ex(&rp->mapA[s], srcs[s].t, 64, R2_ROWS, true);
+        int rc = encode_planes_map_ex(&rp->mapA[s], srcs[s].t, 64, R2_ROWS, 128);
         if (rc) return rc;
         rp->a_col[s] = srcs[s].col0;
     }
