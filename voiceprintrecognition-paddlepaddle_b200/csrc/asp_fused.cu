@@ -79,6 +79,8 @@ __global__ void __launch_bounds__(384, 1) asp_fused_kernel(const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
+    griddep_launch_dependents();  // PDL
+    griddep_wait();
 
     const int slabs = p.C / 128;
     const int items = slabs * p.B;
@@ -310,10 +312,9 @@ int asp_fused_launch(const AspFusedParams& p, int precision, int num_sms, cudaSt
     const int items = (p.C / 128) * p.B;
     const int grid = std::min(items, num_sms);
     if (x3)
-        asp_fused_kernel<3><<<grid, 384, smem, st>>>(p);
+        PPV_PDL_OK(launch_pdl(asp_fused_kernel<3>, dim3(grid), dim3(384), size_t(smem), st, p), "asp_fused_kernel");
     else
-        asp_fused_kernel<1><<<grid, 384, smem, st>>>(p);
-    PPV_LAUNCH_OK("asp_fused_kernel");
+        PPV_PDL_OK(launch_pdl(asp_fused_kernel<1>, dim3(grid), dim3(384), size_t(smem), st, p), "asp_fused_kernel");
     return PPV_OK;
 }
 

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <string>
+#include <utility>
 
 #include "../../include/ppv_b200.h"
 
@@ -30,6 +31,27 @@ int fail(int code, const std::string& msg);
 #define PPV_REQUIRE(cond, msg)                                     \
     do {                                                           \
         if (!(cond)) return ::ppv::fail(PPV_EINVAL, std::string(msg)); \
+    } while (0)
+
+// Launch with programmatic dependent launch enabled (see ptx.cuh: griddep_wait / griddep_launch_dependents).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#define PPV_PDL_OK(call, what)                                                                                     \
+    do {                                                                                                           \
+        cudaError_t _e = (call);                                                                                   \
+        if (_e != cudaSuccess) return ::ppv::fail(PPV_ECUDA, std::string(what) + ": " + cudaGetErrorString(_e));   \
     } while (0)
 
 // ---- activation storage ---------------------------------------------------------------------------
@@ -83,6 +105,7 @@ struct Epilogue {
     int Tp = 0, P = 0, T = 0;
     int halo = 0;  // also write the reflect halo rows (output feeds a dilated conv)
     int f32_vec_ok = 0;  // set by gemm_build: OUT_F32 rows are 16-byte aligned
+    int debug_nostore = 0;  // PPV_GEMM_NOSTORE=1 (tools/gemm_bench.py only): skip the epilogue stores
 };
 
 struct GemmParams {

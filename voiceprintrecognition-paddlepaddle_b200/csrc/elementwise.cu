@@ -33,6 +33,8 @@ __device__ __forceinline__ void st_split2(__nv_bfloat16* hi, __nv_bfloat16* lo, 
 // ------------------------------------------------------------------------------------------------
 // pack_features: one warp per frame row; channels >= F are zero-filled (K padding of the first conv).
 __global__ void pack_features_kernel(const float* __restrict__ feat, int B, int T, int F, Planes out, int P, int Tp) {
+    griddep_launch_dependents();
+    griddep_wait();
     const int warps_per_block = blockDim.x >> 5;
     const int64_t frame = int64_t(blockIdx.x) * warps_per_block + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -57,8 +59,8 @@ __global__ void pack_features_kernel(const float* __restrict__ feat, int B, int 
 int launch_pack_features(const float* feat, int B, int T, int F, const Planes& out, int P, int Tp, cudaStream_t st) {
     const int64_t frames = int64_t(B) * T;
     const int wpb = 8;
-    pack_features_kernel<<<unsigned((frames + wpb - 1) / wpb), wpb * 32, 0, st>>>(feat, B, T, F, out, P, Tp);
-    PPV_LAUNCH_OK("pack_features_kernel");
+    PPV_PDL_OK(launch_pdl(pack_features_kernel, dim3(unsigned((frames + wpb - 1) / wpb)), dim3(wpb * 32), 0, st, feat, B, T, F, out, P, Tp),
+               "pack_features_kernel");
     return PPV_OK;
 }
 
@@ -89,6 +91,8 @@ __global__ void __launch_bounds__(STAT_WARPS * 32)
                     Planes out_pl) {
     __shared__ float s_s[STAT_WARPS][64];
     __shared__ float s_q[STAT_WARPS][64];
+    griddep_launch_dependents();
+    griddep_wait();
     const int b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cg = lane & 7, rsub = lane >> 3;
@@ -176,8 +180,7 @@ int launch_colstats(const Planes& x, int col0, int C, int B, int T, int P, int T
                     const Planes& out_pl, cudaStream_t st) {
     PPV_REQUIRE(C % 64 == 0 && col0 % 8 == 0 && x.ld % 8 == 0, "colstats: C % 64, col0 % 8, ld % 8 required");
     dim3 grid(C / 64, B);
-    colstats_kernel<<<grid, STAT_WARPS * 32, 0, st>>>(x, col0, C, T, P, Tp, mode, eps, out_f32, out_pl);
-    PPV_LAUNCH_OK("colstats_kernel");
+    PPV_PDL_OK(launch_pdl(colstats_kernel, grid, dim3(STAT_WARPS * 32), 0, st, x, col0, C, T, P, Tp, mode, eps, out_f32, out_pl), "colstats_kernel");
     return PPV_OK;
 }
 
@@ -197,6 +200,8 @@ __device__ __forceinline__ void unpack8(const uint4& h, const uint4& l, float (&
 __global__ void __launch_bounds__(256)
     se_scale_res_kernel(Planes z, const float* __restrict__ scale, Planes res, int rc0, Planes out, int oc0, int C, int Tp,
                         int64_t rows) {
+    griddep_launch_dependents();
+    griddep_wait();
     const int groups = C >> 3;
     const int64_t total = rows * groups;
     for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
@@ -230,8 +235,7 @@ int launch_se_scale_res(const Planes& z, const float* scale, const Planes& res, 
     const int64_t total = rows * (C / 8);
     const int64_t want = (total + 255) / 256;
     const int grid = int(std::min<int64_t>(want, int64_t(num_sms) * 16));
-    se_scale_res_kernel<<<grid, 256, 0, st>>>(z, scale, res, rc0, out, oc0, C, Tp, rows);
-    PPV_LAUNCH_OK("se_scale_res_kernel");
+    PPV_PDL_OK(launch_pdl(se_scale_res_kernel, dim3(grid), dim3(256), 0, st, z, scale, res, rc0, out, oc0, C, Tp, rows), "se_scale_res_kernel");
     return PPV_OK;
 }
 

@@ -77,6 +77,8 @@ __global__ void __launch_bounds__(FB_WARPS * 32)
         s_mlen[i] = tb.mel_len[i];
         s_moff[i] = tb.mel_off[i];
     }
+    griddep_launch_dependents();
+    griddep_wait();  // tables above are constants; the waveform / output buffers may be shared with the previous step
     const int seg = (nf - 1) * shift + win;
     const float* src = wav + int64_t(b) * L + int64_t(f0) * shift;
     for (int i = tid; i < seg; i += blockDim.x) s_wav[i] = __ldg(src + i);
@@ -185,6 +187,8 @@ __global__ void __launch_bounds__(FB_WARPS * 32)
 // column means over time: mean[b, f]
 __global__ void __launch_bounds__(256) fbank_mean_kernel(const float* __restrict__ raw, int T, int F, float* __restrict__ mean) {
     __shared__ float s_part[8][FB_MAX_MELS];
+    griddep_launch_dependents();
+    griddep_wait();
     const int b = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float acc[FB_MAX_MELS / 32] = {0.f, 0.f, 0.f, 0.f};
@@ -211,6 +215,8 @@ __global__ void __launch_bounds__(256) fbank_mean_kernel(const float* __restrict
 __global__ void __launch_bounds__(256)
     fbank_finalize_kernel(const float* __restrict__ raw, const float* __restrict__ mean, const float* __restrict__ lens_ratio,
                           int B, int T, int F, float* out_f32, Planes out_pl, int P, int Tp) {
+    griddep_launch_dependents();
+    griddep_wait();
     const int64_t frame = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (frame >= int64_t(B) * T) return;
@@ -392,20 +398,19 @@ int fbank_run(Fbank* h, const float* wav, const float* lens_ratio, int B, int L,
         const float* w = wav + int64_t(b0) * L;
         float* r = raw + int64_t(b0) * T * F;
         dim3 grid((T + FB_FRAMES_PER_BLOCK - 1) / FB_FRAMES_PER_BLOCK, nb);
-        fbank_logmel_kernel<<<grid, FB_WARPS * 32, smem, st>>>(w, L, T, h->win, h->shift, F, h->cfg.preemph, h->cfg.log_floor,
-                                                               h->tb, r);
-        PPV_LAUNCH_OK("fbank_logmel_kernel");
-        fbank_mean_kernel<<<nb, 256, 0, st>>>(r, T, F, h->mean_buf);
-        PPV_LAUNCH_OK("fbank_mean_kernel");
+        PPV_PDL_OK(launch_pdl(fbank_logmel_kernel, grid, dim3(FB_WARPS * 32), smem, st, w, L, T, h->win, h->shift, F, h->cfg.preemph,
+                              h->cfg.log_floor, h->tb, r),
+                   "fbank_logmel_kernel");
+        PPV_PDL_OK(launch_pdl(fbank_mean_kernel, dim3(nb), dim3(256), 0, st, (const float*)r, T, F, h->mean_buf), "fbank_mean_kernel");
         Planes pl = out_pl;
         if (pl.base) {  // rows of this chunk start at b0 * Tp
             pl.base += int64_t(b0) * Tp * pl.ld;
         }
         const int64_t frames = int64_t(nb) * T;
-        fbank_finalize_kernel<<<unsigned((frames + 7) / 8), 256, 0, st>>>(
-            r, h->mean_buf, lens_ratio ? lens_ratio + b0 : nullptr, nb, T, F, out_f32 ? out_f32 + int64_t(b0) * T * F : nullptr, pl,
-            P, Tp);
-        PPV_LAUNCH_OK("fbank_finalize_kernel");
+        PPV_PDL_OK(launch_pdl(fbank_finalize_kernel, dim3(unsigned((frames + 7) / 8)), dim3(256), 0, st, (const float*)r,
+                              (const float*)h->mean_buf, lens_ratio ? lens_ratio + b0 : (const float*)nullptr, nb, T, F,
+                              out_f32 ? out_f32 + int64_t(b0) * T * F : (float*)nullptr, pl, P, Tp),
+                   "fbank_finalize_kernel");
     }
     return PPV_OK;
 }

@@ -55,7 +55,7 @@ __device__ __forceinline__ void epilogue_tile(const Epilogue& ep, int M, int N, 
         tmem_ld32(t_addr + c * 32, v);
         tmem_ld_wait();
         const int col = n0 + c * 32;
-        if (!valid || col >= N) continue;
+        if (!valid || col >= N || ep.debug_nostore) continue;
         float x[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + s_bias[c * 32 + j];

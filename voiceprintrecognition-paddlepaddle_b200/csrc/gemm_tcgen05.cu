@@ -17,6 +17,7 @@
 //                             split-bf16 (or fp32) stores incl. the reflect-halo rows
 // TMEM holds two BN-column fp32 accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -109,6 +110,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
+    griddep_launch_dependents();  // PDL: the next kernel may begin its prologue
+    griddep_wait();               // PDL: upstream activations are complete and visible
 
     const int num_tiles = gp.m_tiles * gp.n_tiles;
     const int nk = gp.num_ksteps;
@@ -292,6 +295,10 @@ int gemm_build(GemmParams* gp, const GemmSource* srcs, int nsrc, const Planes& W
     gp->m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
     gp->n_tiles = (N + BN - 1) / BN;
     gp->epi = epi;
+    {
+        const char* ns = getenv("PPV_GEMM_NOSTORE");
+        gp->epi.debug_nostore = (ns && ns[0] == '1') ? 1 : 0;
+    }
     if (epi.out_mode == OUT_PLANES) {
         PPV_REQUIRE((epi.out_ld % 8) == 0 && (epi.out_col0 % 8) == 0 && (epi.out_plane_stride % 8) == 0,
                     "gemm_build: planes output must be 16-byte aligned");
@@ -312,8 +319,8 @@ static int launch_one(const GemmParams& gp, int num_sms, cudaStream_t stream) {
     }
     const int tiles = gp.m_tiles * gp.n_tiles;
     const int grid = std::min(tiles, num_sms);
-    gemm_tcgen05_kernel<BN, NSPLIT, BK><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(gp);
-    PPV_LAUNCH_OK("gemm_tcgen05_kernel");
+    PPV_PDL_OK(launch_pdl(gemm_tcgen05_kernel<BN, NSPLIT, BK>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, gp),
+               "gemm_tcgen05_kernel");
     return PPV_OK;
 }
 

@@ -153,6 +153,14 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
            | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// launch_dependents: the next kernel in the stream (launched with the programmatic-serialization attribute) may start
+// its prologue (barrier init, TMEM alloc, descriptor prefetch, constant loads) while this grid is still running.
+// wait: blocks until every grid this one depends on has completed and its memory is visible.  EVERY kernel launched
+// through launch_pdl() must execute griddep_wait() before it reads or writes global memory produced upstream.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

@@ -91,6 +91,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) res2conv_kernel(const __grid_
     const uint32_t tmem_base = *tmem_slot_gen;
     const int nsrc = rp.nsrc;
     const int wslices = nsrc * 3;
+    griddep_launch_dependents();  // PDL
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) res2conv_kernel(const __grid_
                 for (int pl = 0; pl < NP; ++pl) tma_load_3d(w_base + (ks * NP + pl) * R2_W_TILE, &rp.mapW, w_full, ks * 64, 0, pl);
         }
         __syncwarp();
+        griddep_wait();  // the weights above are constants; the activations below come from the previous kernel
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < rp.m_tiles; tile += gridDim.x) {
@@ -169,6 +171,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) res2conv_kernel(const __grid_
     } else if (warp >= 4) {
         // ===================== epilogue (shared with the gather-GEMM) =====================
         const int q = warp & 3, etid = threadIdx.x - 128, ehalf = (warp - 4) >> 2;
+        griddep_wait();  // the epilogue writes buffers that upstream kernels may still be reading
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < rp.m_tiles; tile += gridDim.x) {
@@ -215,8 +218,7 @@ static int launch_r2(const Res2Params& rp, int num_sms, cudaStream_t st) {
         attr_set = true;
     }
     const int grid = std::min(rp.m_tiles, num_sms);
-    res2conv_kernel<NSPLIT><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(rp);
-    PPV_LAUNCH_OK("res2conv_kernel");
+    PPV_PDL_OK(launch_pdl(res2conv_kernel<NSPLIT>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, st, rp), "res2conv_kernel");
     return PPV_OK;
 }
 
