@@ -114,6 +114,7 @@ struct GemmParams {
     KStep ksteps[GEMM_MAX_KSTEPS];
     int num_ksteps;
     int bk;  // K elements per k-step (64 or 32)
+    int l2_prefetch;  // producer prefetches the next tile's activation rows into L2
     int M, N;
     int m_tiles, n_tiles;
     Epilogue epi;
@@ -143,6 +144,7 @@ struct Res2Params {
     CUtensorMap mapW;     // weight planes [2][64][nsrc*3*64], box {64, 64, 1}
     int a_col[2];
     int nsrc, dil;
+    int l2_prefetch;
     int M, m_tiles;
     Epilogue epi;
 };

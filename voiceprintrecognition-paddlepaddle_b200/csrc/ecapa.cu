@@ -403,8 +403,8 @@ static int build_plan(EcapaModel* m, int B, int T, void* ws, size_t ws_bytes, cu
     const int64_t R = int64_t(B) * Tp;
     const char* r2env = getenv("PPV_RES2_GEMM");  // debugging aid: 1 = run the Res2Net convs through the generic gather-GEMM
     const bool use_res2_kernel = (w == 64) && !(r2env && r2env[0] == '1');
-    const char* bkenv = getenv("PPV_GEMM_BK64");  // debugging aid: 1 = 64-wide k-steps everywhere
-    const bool bk32_enabled = !(bkenv && bkenv[0] == '1');
+    const char* bkenv = getenv("PPV_GEMM_BK32");  // experiment: 1 = 32-wide k-steps (SWIZZLE_64B) on the wide-N layers; measured slower
+    const bool bk32_enabled = (bkenv && bkenv[0] == '1');
 
     auto add_gemm = [&](const ConvW& cw, const std::vector<KSpec>& ks, const Planes* src_override, int override_col0, int M,
                         Epilogue ep) -> int {

@@ -123,6 +123,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m0 = (tile / gp.n_tiles) * GEMM_BM;
             const int n0 = (tile % gp.n_tiles) * BN;
+            // L2 prefetch of the activation rows of this CTA's NEXT tile (one CTA per m-tile issues it): they come
+            // from HBM, and a 2-4 slot ring alone cannot hide that latency.
+            const int ntile = tile + gridDim.x;
+            if (gp.l2_prefetch && ntile < num_tiles && (ntile % gp.n_tiles) == 0 && lane < nk) {
+                const int nm0 = (ntile / gp.n_tiles) * GEMM_BM;
+                for (int s = lane; s < nk; s += 32) {
+                    const KStep ks = gp.ksteps[s];
+#pragma unroll
+                    for (int p = 0; p < Cfg::NA; ++p) tma_prefetch_l2_3d(&gp.mapA[ks.map], ks.a_col, nm0 + ks.row_off, p);
+                }
+            }
+            __syncwarp();
             for (int s = 0; s < nk; ++s) {
                 mbar_wait(empty_bar(stage), phase ^ 1u);
                 if (lane == 0) {
@@ -298,6 +310,8 @@ int gemm_build(GemmParams* gp, const GemmSource* srcs, int nsrc, const Planes& W
     {
         const char* ns = getenv("PPV_GEMM_NOSTORE");
         gp->epi.debug_nostore = (ns && ns[0] == '1') ? 1 : 0;
+        const char* pf = getenv("PPV_GEMM_NO_L2PREFETCH");
+        gp->l2_prefetch = (pf && pf[0] == '1') ? 0 : 1;
     }
     if (epi.out_mode == OUT_PLANES) {
         PPV_REQUIRE((epi.out_ld % 8) == 0 && (epi.out_col0 % 8) == 0 && (epi.out_plane_stride % 8) == 0,

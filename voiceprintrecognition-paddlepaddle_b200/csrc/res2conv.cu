@@ -12,6 +12,7 @@
 //     valid matrix start with base_offset = 0 (setting base_offset = row mod 8 gives WRONG results).
 // L2 -> SM traffic per 128-row tile: 2 x 2 x 17 KB = 70 KB instead of 288 KB.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.h"
@@ -106,6 +107,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) res2conv_kernel(const __grid_
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < rp.m_tiles; tile += gridDim.x) {
             const int m0 = tile * GEMM_BM;
+            const int ntile = tile + gridDim.x;
+            if (rp.l2_prefetch && ntile < rp.m_tiles && lane < nsrc * NP) {  // next tile's rows: HBM -> L2 ahead of time
+                const int s = lane / NP, pl = lane % NP;
+                tma_prefetch_l2_3d(&rp.mapA[s], rp.a_col[s], ntile * GEMM_BM - R2_PAD, pl);
+            }
+            __syncwarp();
             for (int s = 0; s < nsrc; ++s) {
                 mbar_wait(empty_bar(stage), phase ^ 1u);
                 if (lane == 0) {
@@ -203,6 +210,10 @@ int res2conv_build(Res2Params* rp, const GemmSource* srcs, int nsrc, const Plane
     if (rc) return rc;
     rp->nsrc = nsrc;
     rp->dil = dil;
+    {
+        const char* pf = getenv("PPV_GEMM_NO_L2PREFETCH");
+        rp->l2_prefetch = (pf && pf[0] == '1') ? 0 : 1;
+    }
     rp->M = M;
     rp->m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
     rp->epi = epi;
