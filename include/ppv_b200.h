@@ -155,6 +155,10 @@ int ppv_gemm_test(const float* A, const float* W, const float* bias, const float
                   int relu, int M, int N, int K, int block_n, int block_k, int precision, float* out, void* ws,
                   size_t ws_bytes, void* stream);
 
+/* Kernel-only timing of the gather-GEMM (tools/gemm_bench.py); ws >= 4*(pad128(M)*pad64(K) + pad256(N)*pad64(K) + pad128(M)*N) bytes. */
+int ppv_gemm_bench(int M, int N, int K, int block_n, int block_k, int precision, int planes_out, int iters, void* ws,
+                   size_t ws_bytes, float* ms_per_launch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -279,4 +279,52 @@ int ppv_gemm_test(const float* A, const float* W, const float* bias, const float
     PPV_GUARD_END
 }
 
+// Kernel-only timing of the gather-GEMM (tools/gemm_bench.py): operands are converted once, the kernel is launched
+// `iters` times between two CUDA events on `stream`; *ms_per_launch receives the average.  out is fp32 [M,N] or, when
+// planes_out != 0, a split-bf16 planes buffer inside ws (the layout every model layer writes).
+int ppv_gemm_bench(int M, int N, int K, int block_n, int block_k, int precision, int planes_out, int iters, void* ws, size_t ws_bytes,
+                   float* ms_per_launch, void* stream) {
+    PPV_GUARD_BEGIN
+    PPV_REQUIRE(ws && ms_per_launch && iters > 0, "ppv_gemm_bench: bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t Kp = au(size_t(K), 64);
+    const size_t a_bytes = au(au(size_t(M), 128) * Kp * 4, 256), w_bytes = au(au(size_t(N), 256) * Kp * 4, 256);
+    const size_t o_bytes = au(au(size_t(M), 128) * size_t(N) * 4, 256);
+    PPV_REQUIRE(ws_bytes >= a_bytes + w_bytes + o_bytes, "ppv_gemm_bench: workspace too small");
+    Planes pa, pw, po;
+    pa.rows = int64_t(au(size_t(M), 128)); pa.ld = int(Kp); pa.plane_stride = pa.rows * pa.ld; pa.base = static_cast<__nv_bfloat16*>(ws);
+    pw.rows = int64_t(au(size_t(N), 256)); pw.ld = int(Kp); pw.plane_stride = pw.rows * pw.ld;
+    pw.base = reinterpret_cast<__nv_bfloat16*>(static_cast<uint8_t*>(ws) + a_bytes);
+    po.rows = pa.rows; po.ld = N; po.plane_stride = po.rows * po.ld;
+    po.base = reinterpret_cast<__nv_bfloat16*>(static_cast<uint8_t*>(ws) + a_bytes + w_bytes);
+    PPV_CUDA_OK(cudaMemsetAsync(ws, 0x11, a_bytes + w_bytes, st));  // small finite bf16 values
+    GemmSource src{pa, 0, int(Kp), 0};
+    Epilogue ep;
+    ep.relu = 1;
+    if (planes_out) {
+        ep.out_mode = OUT_PLANES; ep.out = po.base; ep.out_ld = po.ld; ep.out_plane_stride = po.plane_stride;
+    } else {
+        ep.out_mode = OUT_F32; ep.out = po.base; ep.out_ld = N;
+    }
+    GemmParams gp;
+    int rc = gemm_build(&gp, &src, 1, pw, M, N, ep, block_n, block_k);
+    if (rc) return rc;
+    const int sms = device_sm_count();
+    for (int i = 0; i < 3; ++i) { rc = gemm_launch(gp, block_n, precision, sms, st); if (rc) return rc; }
+    cudaEvent_t e0, e1;
+    PPV_CUDA_OK(cudaEventCreate(&e0));
+    PPV_CUDA_OK(cudaEventCreate(&e1));
+    PPV_CUDA_OK(cudaEventRecord(e0, st));
+    for (int i = 0; i < iters; ++i) { rc = gemm_launch(gp, block_n, precision, sms, st); if (rc) return rc; }
+    PPV_CUDA_OK(cudaEventRecord(e1, st));
+    PPV_CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    PPV_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ms_per_launch = ms / float(iters);
+    return PPV_OK;
+    PPV_GUARD_END
+}
+
 }  // extern "C"

@@ -104,7 +104,7 @@ struct Epilogue {
     // row validity: Tp == 0 -> rows [0, M) are all valid (plain matrix); else padded time layout.
     int Tp = 0, P = 0, T = 0;
     int halo = 0;  // also write the reflect halo rows (output feeds a dilated conv)
-    int f32_vec_ok = 0;  // set by gemm_build: OUT_F32 rows are 16-byte aligned
+    int f32_vec_ok = 0;  // set by gemm_build: OUT_F32 rows are 16-byte (1) / 32-byte (2) aligned
     int debug_nostore = 0;  // PPV_GEMM_NOSTORE=1 (tools/gemm_bench.py only): skip the epilogue stores
 };
 

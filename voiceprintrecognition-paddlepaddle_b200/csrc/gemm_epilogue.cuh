@@ -88,7 +88,13 @@ __device__ __forceinline__ void epilogue_tile(const Epilogue& ep, int M, int N, 
         }
         if (ep.out_mode == OUT_F32) {
             float* dstf = static_cast<float*>(ep.out) + row * ep.out_ld + ep.out_col0 + col;
-            if (ep.f32_vec_ok && col + 32 <= N) {
+            if (ep.f32_vec_ok == 2 && col + 32 <= N) {  // 32-byte aligned rows: full-sector stores
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    st_global_v8(dstf + 8 * j, __float_as_uint(x[8 * j]), __float_as_uint(x[8 * j + 1]), __float_as_uint(x[8 * j + 2]),
+                                 __float_as_uint(x[8 * j + 3]), __float_as_uint(x[8 * j + 4]), __float_as_uint(x[8 * j + 5]),
+                                 __float_as_uint(x[8 * j + 6]), __float_as_uint(x[8 * j + 7]));
+            } else if (ep.f32_vec_ok && col + 32 <= N) {
                 float4* dst = reinterpret_cast<float4*>(dstf);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) dst[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
@@ -108,13 +114,15 @@ __device__ __forceinline__ void epilogue_tile(const Epilogue& ep, int M, int N, 
                 l[j] = pack_bf16x2(l0, l1);
             }
             __nv_bfloat16* obase = static_cast<__nv_bfloat16*>(ep.out) + ep.out_col0 + col;
-            auto store_row = [&](int64_t r) {
-                uint4* ph = reinterpret_cast<uint4*>(obase + r * ep.out_ld);
-                uint4* pl = reinterpret_cast<uint4*>(obase + ep.out_plane_stride + r * ep.out_ld);
+            auto store_row = [&](int64_t r) {  // 64 B per plane = two full 32-byte sectors
+                __nv_bfloat16* ph = obase + r * ep.out_ld;
+                __nv_bfloat16* pl = ph + ep.out_plane_stride;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    ph[j] = make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
-                    pl[j] = make_uint4(l[4 * j], l[4 * j + 1], l[4 * j + 2], l[4 * j + 3]);
+                for (int j = 0; j < 2; ++j) {
+                    st_global_v8(ph + 16 * j, h[8 * j], h[8 * j + 1], h[8 * j + 2], h[8 * j + 3], h[8 * j + 4], h[8 * j + 5], h[8 * j + 6],
+                                 h[8 * j + 7]);
+                    st_global_v8(pl + 16 * j, l[8 * j], l[8 * j + 1], l[8 * j + 2], l[8 * j + 3], l[8 * j + 4], l[8 * j + 5], l[8 * j + 6],
+                                 l[8 * j + 7]);
                 }
             };
             store_row(row);

@@ -314,10 +314,12 @@ int gemm_build(GemmParams* gp, const GemmSource* srcs, int nsrc, const Planes& W
         gp->l2_prefetch = (pf && pf[0] == '1') ? 0 : 1;
     }
     if (epi.out_mode == OUT_PLANES) {
-        PPV_REQUIRE((epi.out_ld % 8) == 0 && (epi.out_col0 % 8) == 0 && (epi.out_plane_stride % 8) == 0,
-                    "gemm_build: planes output must be 16-byte aligned");
+        PPV_REQUIRE((epi.out_ld % 16) == 0 && (epi.out_col0 % 16) == 0 && (epi.out_plane_stride % 16) == 0 &&
+                        (reinterpret_cast<uintptr_t>(epi.out) & 31) == 0,
+                    "gemm_build: planes output must be 32-byte aligned (256-bit stores)");
     } else {
         gp->epi.f32_vec_ok = ((epi.out_ld % 4) == 0 && (epi.out_col0 % 4) == 0 && (reinterpret_cast<uintptr_t>(epi.out) & 15) == 0) ? 1 : 0;
+        if ((epi.out_ld % 8) == 0 && (epi.out_col0 % 8) == 0 && (reinterpret_cast<uintptr_t>(epi.out) & 31) == 0) gp->epi.f32_vec_ok = 2;
     }
     return PPV_OK;
 }

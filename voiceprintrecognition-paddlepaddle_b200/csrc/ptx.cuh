@@ -169,6 +169,16 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// 256-bit global store (sm_100+): one full 32-byte sector per thread per instruction.  The epilogues write rows that are
+// 1-3 KB apart, so a warp-wide 16-byte store touches 32 half sectors; measured on B200 that halves the L1->L2 write
+// efficiency and makes the K=512 GEMM layers store-bound.  p must be 32-byte aligned.
+__device__ __forceinline__ void st_global_v8(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f,
+                                             uint32_t g, uint32_t h) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e),
+                 "r"(f), "r"(g), "r"(h)
+                 : "memory");
+}
+
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
