@@ -105,12 +105,14 @@ struct Epilogue {
     int Tp = 0, P = 0, T = 0;
     int halo = 0;  // also write the reflect halo rows (output feeds a dilated conv)
     int f32_vec_ok = 0;  // set by gemm_build: OUT_F32 rows are 16-byte (1) / 32-byte (2) aligned
+    int tma_store = 0;   // set by gemm_build: planes output without halo goes through a shared-memory staging tile + TMA store
     int debug_nostore = 0;  // PPV_GEMM_NOSTORE=1 (tools/gemm_bench.py only): skip the epilogue stores
 };
 
 struct GemmParams {
     CUtensorMap mapA[GEMM_MAX_MAPS];
     CUtensorMap mapB;
+    CUtensorMap mapOut;  // output planes, box {64, 128, 1}, SWIZZLE_128B (TMA-store epilogue)
     KStep ksteps[GEMM_MAX_KSTEPS];
     int num_ksteps;
     int bk;  // K elements per k-step (64 or 32)

@@ -11,26 +11,68 @@ namespace ppv {
 constexpr int GEMM_EPI_THREADS = 256;                 // 8 epilogue warps
 constexpr int GEMM_THREADS = 128 + GEMM_EPI_THREADS;  // + TMA, MMA, TMEM-alloc, spare warps
 
-template <int BN>
-__device__ __forceinline__ void epilogue_tile(const Epilogue& ep, int M, int N, int m0, int n0, uint32_t tmem_acc, uint32_t tfull_bar,
-                                              uint32_t acc_phase, uint32_t tempty_bar, int q, int lane, int ehalf, int etid,
-                                              float* s_vec) {
-    float* s_bias = s_vec;
-    float* s_scale = s_vec + BN;
-    float* s_shift = s_vec + 2 * BN;
-    // stage the per-column vectors of this N slice
-    named_bar_sync(1, GEMM_EPI_THREADS);
-    for (int i = etid; i < BN; i += GEMM_EPI_THREADS) {
-        const int n = n0 + i;
-        const bool ok = n < N;
-        s_bias[i] = (ep.bias && ok) ? __ldg(ep.bias + n) : 0.f;
-        s_scale[i] = (ep.bn_scale && ok) ? __ldg(ep.bn_scale + n) : 1.f;
-        s_shift[i] = (ep.bn_shift && ok) ? __ldg(ep.bn_shift + n) : 0.f;
-    }
-    named_bar_sync(1, GEMM_EPI_THREADS);
+constexpr int EPI_STAGING_BYTES = 2 * GEMM_BM * 128;  // [hi | lo] x 128 rows x 64 bf16 columns, SWIZZLE_128B
 
+// per-column epilogue math on 32 accumulator columns starting at global column `col`
+__device__ __forceinline__ void epilogue_math(const Epilogue& ep, int N, int col, int64_t grp, const uint32_t (&v)[32], float (&x)[32]) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+    if (ep.bias) {
+        const float4* b = reinterpret_cast<const float4*>(ep.bias + col);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 b4 = __ldg(b + j);
+            x[4 * j + 0] += b4.x;
+            x[4 * j + 1] += b4.y;
+            x[4 * j + 2] += b4.z;
+            x[4 * j + 3] += b4.w;
+        }
+    }
+    if (ep.rowgrp_bias) {
+        const float4* rg = reinterpret_cast<const float4*>(ep.rowgrp_bias + grp * N + col);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 b4 = __ldg(rg + j);
+            x[4 * j + 0] += b4.x;
+            x[4 * j + 1] += b4.y;
+            x[4 * j + 2] += b4.z;
+            x[4 * j + 3] += b4.w;
+        }
+    }
+    if (ep.relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+    }
+    if (ep.bn_scale) {
+        const float4* sc = reinterpret_cast<const float4*>(ep.bn_scale + col);
+        const float4* sh = reinterpret_cast<const float4*>(ep.bn_shift + col);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 a = __ldg(sc + j), b = __ldg(sh + j);
+            x[4 * j + 0] = fmaf(x[4 * j + 0], a.x, b.x);
+            x[4 * j + 1] = fmaf(x[4 * j + 1], a.y, b.y);
+            x[4 * j + 2] = fmaf(x[4 * j + 2], a.z, b.z);
+            x[4 * j + 3] = fmaf(x[4 * j + 3], a.w, b.w);
+        }
+    }
+    if (ep.tanh_) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = tanhf(x[j]);
+    }
+    if (ep.sigmoid_) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = 1.f / (1.f + expf(-x[j]));
+    }
+}
+
+// `staging`: shared-memory address (1024-aligned) of EPI_STAGING_BYTES for the TMA-store path, 0 if unavailable.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const Epilogue& ep, const CUtensorMap* map_out, int M, int N, int m0, int n0,
+                                              uint32_t tmem_acc, uint32_t tfull_bar, uint32_t acc_phase, uint32_t tempty_bar, int q,
+                                              int lane, int ehalf, int etid, uint32_t staging, uint8_t* staging_gen) {
     // row bookkeeping
-    const int64_t row = int64_t(m0) + q * 32 + lane;
+    const int rloc = q * 32 + lane;  // row within the tile == TMEM lane
+    const int64_t row = int64_t(m0) + rloc;
     bool valid = row < M;
     int64_t mirror_a = -1, mirror_b = -1;
     int64_t grp = 0;
@@ -48,6 +90,57 @@ __device__ __forceinline__ void epilogue_tile(const Epilogue& ep, int M, int N, 
     mbar_wait(tfull_bar, acc_phase);
     tc_fence_after();
     const uint32_t t_addr = tmem_acc + (uint32_t(q * 32) << 16);
+
+    if (ep.tma_store && staging != 0) {
+        // ---- planes output without halo: 64-column slabs through a swizzled staging tile, written out by TMA with full
+        // 128-byte lines.  Garbage rows (time padding, rows >= M) are stored too: their consumers never read them.
+        const int64_t gsafe = valid ? grp : 0;
+#pragma unroll 1
+        for (int s = 0; s < BN / 64; ++s) {
+            const int c = 2 * s + ehalf;
+            const int col = n0 + c * 32;
+            uint32_t v[32];
+            __syncwarp();
+            tmem_ld32(t_addr + c * 32, v);
+            tmem_ld_wait();
+            float x[32];
+            if (col < N) {
+                epilogue_math(ep, N, col, gsafe, v, x);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) x[j] = 0.f;
+            }
+            if (etid == 0) bulk_wait_read0();  // the previous slab's TMA stores have drained the staging tile
+            named_bar_sync(1, GEMM_EPI_THREADS);
+            uint8_t* sh = staging_gen + rloc * 128;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {  // four 16-byte chunks (8 columns each) of this thread's 32 columns
+                uint32_t hw[4], lw[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    __nv_bfloat16 h0, l0, h1, l1;
+                    split_bf16(x[8 * k + 2 * j], h0, l0);
+                    split_bf16(x[8 * k + 2 * j + 1], h1, l1);
+                    hw[j] = pack_bf16x2(h0, h1);
+                    lw[j] = pack_bf16x2(l0, l1);
+                }
+                const int chunk = ((ehalf * 4 + k) ^ (rloc & 7)) << 4;  // SWIZZLE_128B: 16-byte chunk index XOR (row mod 8)
+                *reinterpret_cast<uint4*>(sh + chunk) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                *reinterpret_cast<uint4*>(sh + GEMM_BM * 128 + chunk) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(1, GEMM_EPI_THREADS);
+            if (etid == 0 && n0 + s * 64 < N && !ep.debug_nostore) {
+                tma_store_3d(map_out, staging, ep.out_col0 + n0 + s * 64, m0, 0);
+                tma_store_3d(map_out, staging + GEMM_BM * 128, ep.out_col0 + n0 + s * 64, m0, 1);
+                bulk_commit_group();
+            }
+        }
+        tc_fence_before();
+        mbar_arrive(tempty_bar);
+        return;
+    }
+
 #pragma unroll 1
     for (int c = ehalf; c < BN / 32; c += GEMM_EPI_THREADS / 128) {
         uint32_t v[32];
@@ -57,34 +150,11 @@ __device__ __forceinline__ void epilogue_tile(const Epilogue& ep, int M, int N, 
         const int col = n0 + c * 32;
         if (!valid || col >= N || ep.debug_nostore) continue;
         float x[32];
+        if (col + 32 <= N) {
+            epilogue_math(ep, N, col, grp, v, x);
+        } else {  // ragged N (cosine scoring): no per-column vectors on this path
 #pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + s_bias[c * 32 + j];
-        if (ep.rowgrp_bias) {
-            const float4* rg = reinterpret_cast<const float4*>(ep.rowgrp_bias + grp * N + col);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float4 b4 = __ldg(rg + j);
-                x[4 * j + 0] += b4.x;
-                x[4 * j + 1] += b4.y;
-                x[4 * j + 2] += b4.z;
-                x[4 * j + 3] += b4.w;
-            }
-        }
-        if (ep.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
-        }
-        if (ep.bn_scale) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = fmaf(x[j], s_scale[c * 32 + j], s_shift[c * 32 + j]);
-        }
-        if (ep.tanh_) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = tanhf(x[j]);
-        }
-        if (ep.sigmoid_) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = 1.f / (1.f + expf(-x[j]));
+            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
         }
         if (ep.out_mode == OUT_F32) {
             float* dstf = static_cast<float*>(ep.out) + row * ep.out_ld + ep.out_col0 + col;

@@ -39,12 +39,12 @@ struct GemmCfg {
     static constexpr int A_BYTES = GEMM_BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = NA * A_BYTES + NB * B_BYTES;
-    static constexpr int VEC_BYTES = 3 * BN * 4;  // bias / bn_scale / bn_shift slices
+    static constexpr int STAGING_BYTES = EPI_STAGING_BYTES;  // TMA-store epilogue staging tile
     static constexpr int BAR_BYTES = 256;
     static constexpr int MAX_SMEM = 232448;  // 227 KB
-    static constexpr int STAGES_RAW = (MAX_SMEM - 1024 - VEC_BYTES - BAR_BYTES) / STAGE_BYTES;
+    static constexpr int STAGES_RAW = (MAX_SMEM - 1024 - STAGING_BYTES - BAR_BYTES) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + VEC_BYTES + BAR_BYTES;
+    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES;
     static constexpr int TMEM_COLS = 2 * BN;  // 128 / 256 / 512: power of two >= 32
     static_assert(STAGES >= 2, "need at least a double buffer");
     static_assert(BN == 64 || BN == 128 || BN == 256, "BN");
@@ -73,8 +73,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
     const uint32_t tiles_base = smem_base;
-    float* s_vec = reinterpret_cast<float*>(smem_gen + STAGES * Cfg::STAGE_BYTES);
-    const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES + Cfg::VEC_BYTES;
+    const uint32_t staging = smem_base + STAGES * Cfg::STAGE_BYTES;  // 1024-aligned (stage sizes are multiples of 1024)
+    uint8_t* staging_gen = smem_gen + STAGES * Cfg::STAGE_BYTES;
+    const uint32_t bar_base = staging + Cfg::STAGING_BYTES;
     // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
     volatile uint32_t* tmem_slot_gen =
-        reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + Cfg::VEC_BYTES + 8 * (2 * STAGES + 4));
+        reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + Cfg::STAGING_BYTES + 8 * (2 * STAGES + 4));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < GEMM_MAX_MAPS; ++i) prefetch_tmap(&gp.mapA[i]);
         prefetch_tmap(&gp.mapB);
+        if (gp.epi.tma_store) prefetch_tmap(&gp.mapOut);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -211,11 +213,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m0 = (tile / gp.n_tiles) * GEMM_BM;
             const int n0 = (tile % gp.n_tiles) * BN;
-            epilogue_tile<BN>(gp.epi, gp.M, gp.N, m0, n0, tmem_base + acc * BN, tfull_bar(acc), acc_phase, tempty_bar(acc), q, lane, ehalf,
-                              etid, s_vec);
+            epilogue_tile<BN>(gp.epi, &gp.mapOut, gp.M, gp.N, m0, n0, tmem_base + acc * BN, tfull_bar(acc), acc_phase, tempty_bar(acc), q,
+                              lane, ehalf, etid, staging, staging_gen);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
         }
+        if (etid == 0) bulk_wait_all();  // TMA stores issued by this thread have completed before the CTA retires
     }
 
     tc_fence_before();
@@ -312,6 +315,21 @@ int gemm_build(GemmParams* gp, const GemmSource* srcs, int nsrc, const Planes& W
         gp->epi.debug_nostore = (ns && ns[0] == '1') ? 1 : 0;
         const char* pf = getenv("PPV_GEMM_NO_L2PREFETCH");
         gp->l2_prefetch = (pf && pf[0] == '1') ? 0 : 1;
+    }
+    if (epi.out_mode == OUT_PLANES && !epi.halo && (N % 64) == 0) {
+        const char* nt = getenv("PPV_GEMM_NO_TMASTORE");
+        if (!(nt && nt[0] == '1')) {
+            Planes po;
+            po.base = static_cast<__nv_bfloat16*>(epi.out);
+            po.ld = int(epi.out_ld);
+            po.plane_stride = epi.out_plane_stride;
+            po.rows = epi.out_plane_stride / epi.out_ld;  // planes are allocated back to back
+            if (po.rows * po.ld == po.plane_stride && (epi.out_col0 % 8) == 0) {
+                rc = encode_planes_map_ex(&gp->mapOut, po, 64, GEMM_BM, 128);
+                if (rc) return rc;
+                gp->epi.tma_store = 1;
+            }
+        }
     }
     if (epi.out_mode == OUT_PLANES) {
         PPV_REQUIRE((epi.out_ld % 16) == 0 && (epi.out_col0 % 16) == 0 && (epi.out_plane_stride % 16) == 0 &&

@@ -32,9 +32,8 @@ struct R2Cfg {
     static constexpr int NP = (NSPLIT == 3) ? 2 : 1;
     static constexpr int W_BYTES = 6 * NP * R2_W_TILE;  // room for 2 sources x 3 taps
     static constexpr int STAGE_BYTES = NP * R2_A_SLOT;
-    static constexpr int VEC_BYTES = 3 * 64 * 4;
     static constexpr int STAGES = (NSPLIT == 3) ? 3 : 4;
-    static constexpr int SMEM_BYTES = 1024 + W_BYTES + STAGES * STAGE_BYTES + VEC_BYTES + 256;
+    static constexpr int SMEM_BYTES = 1024 + W_BYTES + STAGES * STAGE_BYTES + 256;
 };
 
 // descriptor for rows [roff, roff+128) of a tall SWIZZLE_128B tile whose slot is 1024-byte aligned
@@ -54,8 +53,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) res2conv_kernel(const __grid_
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
     const uint32_t w_base = smem_base;
     const uint32_t a_base = smem_base + Cfg::W_BYTES;
-    float* s_vec = reinterpret_cast<float*>(smem_gen + Cfg::W_BYTES + STAGES * Cfg::STAGE_BYTES);
-    const uint32_t bar_base = a_base + STAGES * Cfg::STAGE_BYTES + Cfg::VEC_BYTES;
+    const uint32_t bar_base = a_base + STAGES * Cfg::STAGE_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
@@ -182,8 +180,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) res2conv_kernel(const __grid_
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < rp.m_tiles; tile += gridDim.x) {
-            epilogue_tile<BN>(rp.epi, rp.M, BN, tile * GEMM_BM, 0, tmem_base + acc * BN, tfull_bar(acc), acc_phase, tempty_bar(acc), q, lane,
-                              ehalf, etid, s_vec);
+            epilogue_tile<BN>(rp.epi, nullptr, rp.M, BN, tile * GEMM_BM, 0, tmem_base + acc * BN, tfull_bar(acc), acc_phase, tempty_bar(acc),
+                              q, lane, ehalf, etid, 0u, nullptr);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
         }
