@@ -29,6 +29,7 @@ constexpr int AF_A_TILE = 128 * 64 * 2;           // weight tile  [128 ch x 64 k
 constexpr int AF_B_TILE = AF_NT * 64 * 2;         // att tile     [64 fr x 64 k]   bf16, SWIZZLE_128B
 constexpr int AF_X_TILE = AF_NT * 128 * 2;        // x tile       [64 fr x 128 ch] bf16, no swizzle (one plane)
 constexpr int AF_STAGES = 2;
+constexpr float LOG2E = 1.4426950408889634f;
 
 template <int NSPLIT>
 __global__ void __launch_bounds__(384, 1) asp_fused_kernel(const __grid_constant__ AspFusedParams p) {
@@ -198,29 +199,38 @@ __global__ void __launch_bounds__(384, 1) asp_fused_kernel(const __grid_constant
                     tmem_ld_wait();
                     const int nvalid = min(32, p.T - t0);  // warp-uniform
                     if (nvalid > 0) {
-                        float cm = -INFINITY;
+                        // chunk max as a 4-way tree (the serial fmax chain is latency-bound with 2 warps per scheduler)
+                        float cm4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
-                            if (j < nvalid) cm = fmaxf(cm, __uint_as_float(v[j]));
+                            if (j < nvalid) cm4[j & 3] = fmaxf(cm4[j & 3], __uint_as_float(v[j]));
+                        const float cm = fmaxf(fmaxf(cm4[0], cm4[1]), fmaxf(cm4[2], cm4[3]));
                         if (cm > m) {
-                            const float r = __expf(m - cm);  // exp(-inf) = 0 on the first chunk
+                            const float r = exp2f((m - cm) * LOG2E);  // exp(-inf) = 0 on the first chunk
                             S0 *= r;
                             S1 *= r;
                             S2 *= r;
                             m = cm;
                         }
+                        // four independent accumulator sets (ILP), exp as one FFMA + ex2.approx
+                        const float ms = m * LOG2E;
+                        float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             if (j < nvalid) {
                                 const int o = (ch * 32 + j) * 128 + cl;
                                 const float xv = __bfloat162float(xs_hi[o]) + __bfloat162float(xs_lo[o]);
-                                const float e = __expf(__uint_as_float(v[j]) - m);
+                                const float e = exp2f(fmaf(__uint_as_float(v[j]), LOG2E, -ms));
                                 const float d = xv - g;
-                                S0 += e;
-                                S1 = fmaf(e, d, S1);
-                                S2 = fmaf(e * d, d, S2);
+                                const float ed = e * d;
+                                a0[j & 3] += e;
+                                a1[j & 3] += ed;
+                                a2[j & 3] = fmaf(ed, d, a2[j & 3]);
                             }
                         }
+                        S0 += (a0[0] + a0[1]) + (a0[2] + a0[3]);
+                        S1 += (a1[0] + a1[1]) + (a1[2] + a1[3]);
+                        S2 += (a2[0] + a2[1]) + (a2[2] + a2[3]);
                     }
                 }
                 tc_fence_before();
@@ -239,7 +249,7 @@ __global__ void __launch_bounds__(384, 1) asp_fused_kernel(const __grid_constant
             if (half == 0) {
                 const float4 o = s_merge[cl];
                 const float mm = fmaxf(m, o.x);
-                const float ra = __expf(m - mm), rb = (o.y > 0.f) ? __expf(o.x - mm) : 0.f;
+                const float ra = exp2f((m - mm) * LOG2E), rb = (o.y > 0.f) ? exp2f((o.x - mm) * LOG2E) : 0.f;
                 S0 = S0 * ra + o.y * rb;
                 S1 = S1 * ra + o.z * rb;
                 S2 = S2 * ra + o.w * rb;

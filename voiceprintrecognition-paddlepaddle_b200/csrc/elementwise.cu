@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(STAT_WARPS * 32)
     load8(row0, k);
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
-#pragma unroll 2
+#pragma unroll 4
     for (int t = warp * 4 + rsub; t < T; t += STAT_WARPS * 4) {
         float v[8];
         load8(row0 + t, v);
