@@ -91,17 +91,29 @@ __global__ void __launch_bounds__(384, 1) asp_fused_kernel(const __grid_constant
         // ===================== TMA producer =====================
         int stage = 0;
         uint32_t phase = 0, a_phase = 0;
+        int cur_slab = -1;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
             const int slab = item / p.B, b = item - slab * p.B;
-            mbar_wait(a_empty, a_phase ^ 1u);
-            if (lane == 0) {
-                mbar_arrive_expect_tx(a_full, a_bytes);
-                for (int ks = 0; ks < ksteps; ++ks)
-                    for (int pl = 0; pl < NP; ++pl)
-                        tma_load_3d(a_base + (ks * NP + pl) * AF_A_TILE, &p.mapW, a_full, ks * 64, slab * 128, pl);
+            if (slab != cur_slab) {  // the weight slab stays in shared memory while consecutive items share it
+                mbar_wait(a_empty, a_phase ^ 1u);
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(a_full, a_bytes);
+                    for (int ks = 0; ks < ksteps; ++ks)
+                        for (int pl = 0; pl < NP; ++pl)
+                            tma_load_3d(a_base + (ks * NP + pl) * AF_A_TILE, &p.mapW, a_full, ks * 64, slab * 128, pl);
+                }
+                __syncwarp();
+                a_phase ^= 1u;
+                cur_slab = slab;
             }
-            __syncwarp();
-            a_phase ^= 1u;
+            {  // pull the NEXT item's x tiles (HBM) into L2 while this item is processed
+                const int nitem = item + gridDim.x;
+                if (nitem < items && lane < 2 * ntiles) {
+                    const int nslab = nitem / p.B, nb = nitem - nslab * p.B;
+                    tma_prefetch_l2_3d(&p.mapX, nslab * 128, nb * p.Tp + p.P + (lane >> 1) * AF_NT, lane & 1);
+                }
+                __syncwarp();
+            }
             const int row0 = b * p.Tp + p.P;
             for (int ft = 0; ft < ntiles; ++ft) {
                 mbar_wait(b_empty(stage), phase ^ 1u);
@@ -126,9 +138,16 @@ __global__ void __launch_bounds__(384, 1) asp_fused_kernel(const __grid_constant
         constexpr uint32_t idesc = make_idesc_bf16(128, AF_NT);
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0, a_phase = 0;
+        int cur_slab = -1;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
-            mbar_wait(a_full, a_phase);
-            a_phase ^= 1u;
+            const int slab = item / p.B;
+            if (slab != cur_slab) {
+                mbar_wait(a_full, a_phase);
+                a_phase ^= 1u;
+                cur_slab = slab;
+            }
+            const int nitem = item + gridDim.x;
+            const bool last_of_slab = (nitem >= items) || (nitem / p.B != slab);
             for (int ft = 0; ft < ntiles; ++ft) {
                 mbar_wait(tempty(acc), acc_phase ^ 1u);
                 mbar_wait(b_full(stage), phase);
@@ -156,7 +175,7 @@ __global__ void __launch_bounds__(384, 1) asp_fused_kernel(const __grid_constant
                     }
                     umma_commit(b_empty(stage));  // one of the 129 arrivals: the att tiles are consumed
                     umma_commit(tfull(acc));
-                    if (ft == ntiles - 1) umma_commit(a_empty);  // weight slab free once the item's MMAs retire
+                    if (ft == ntiles - 1 && last_of_slab) umma_commit(a_empty);  // weight slab free once its last item's MMAs retire
                 }
                 __syncwarp();
                 if (++stage == AF_STAGES) {
