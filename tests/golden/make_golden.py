@@ -100,6 +100,20 @@ def main():
     Bm = torch.randn(23, 192, generator=g, dtype=torch.float64).numpy()
     h["cos_A"], h["cos_B"], h["cos_AB"] = A, Bm, head.cosine_matrix(A, Bm)
     np.savez_compressed(f"{OUT}/head_seed1000.npz", **h)
+
+    # ---- EER / minDCF: produced by the REFERENCE's own ppvector/metric/metrics.py (pure numpy, importable here)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_metrics", f"{REF}/ppvector/metric/metrics.py")
+    ref_metrics = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_metrics)
+    rng = np.random.default_rng(1000)
+    scores = rng.standard_normal(5000).astype(np.float32) * 0.2
+    labels = (rng.random(5000) < 0.05).astype(np.int32)
+    scores[labels == 1] += 0.45
+    fnr, fpr, thr = ref_metrics.compute_fnr_fpr(scores, labels)
+    eer, eer_thr = ref_metrics.compute_eer(fnr, fpr, scores)
+    np.savez_compressed(f"{OUT}/metrics_ref.npz", scores=scores, labels=labels, eer=float(eer), threshold=float(eer_thr),
+                        min_dcf=float(ref_metrics.compute_dcf(fnr, fpr)), fnr_head=fnr[:50], fpr_tail=fpr[-50:])
     print("losses", {k: float(v) for k, v in h.items() if k.startswith("loss")})
 
 
