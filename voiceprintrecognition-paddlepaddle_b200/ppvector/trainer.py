@@ -55,8 +55,8 @@ class PPVectorTrainer(object):
     # ---- trainer.py:134-157 ------------------------------------------------------------------------------------
     def extract_features(self, save_dir='dataset/features', max_duration=100):
         fz = self._featurizer()
-        for data_list in [self.configs.dataset_conf.train_list, self.configs.dataset_conf.enroll_list,
-                          self.configs.dataset_conf.trials_list]:
+        for list_idx, data_list in enumerate([self.configs.dataset_conf.train_list, self.configs.dataset_conf.enroll_list,
+                                              self.configs.dataset_conf.trials_list]):
             if not os.path.exists(data_list):
                 logger.warning(f'{data_list} 不存在，跳过')
                 continue
@@ -68,8 +68,8 @@ class PPVectorTrainer(object):
             with open(save_data_list, 'w', encoding='utf-8') as f:
                 for i in tqdm(range(len(dataset))):
                     feature, label = dataset[i]
-                    # the reference names files by millisecond timestamps (collisions once extraction is fast): use a counter
-                    save_path = os.path.join(save_dir, str(label), f'{i:08d}.npy').replace('\\', '/')
+                    # the reference names files by millisecond timestamps (collisions once extraction is fast): use counters
+                    save_path = os.path.join(save_dir, str(label), f'{list_idx}_{i:08d}.npy').replace('\\', '/')
                     os.makedirs(os.path.dirname(save_path), exist_ok=True)
                     np.save(save_path, feature.cpu().numpy())
                     f.write(f'{save_path}\t{label}\n')
