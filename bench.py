@@ -245,6 +245,12 @@ def main():
         peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16, kernel timed inside a long step)" if peaks else \
             "fallback 1.4 PF sustained (B200_PROFILING.md)"
+        traffic, traffic_src = None, None
+        try:  # per-launch DRAM bytes of the tensor-core kernels from the committed ncu --set full capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+            traffic, traffic_src = tj["traffic_bytes_per_launch"], tj["source"]
+        except Exception:
+            pass
         flops_step = algorithmic_flops_per_utt() * BATCH
         gemm_s_per_step = g_ms.value / 1000.0 / args.steps
         achieved = flops_step / gemm_s_per_step / 1e12
@@ -265,7 +271,8 @@ def main():
             "gpu_launches": int(g_n.value + o_n.value),
             "clocks": clk,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                         "traffic": None, "kernel": "gemm_tcgen05_kernel (all conv / linear layers)",
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": "tcgen05 gather-GEMM family: gemm_tcgen05_kernel + res2conv_kernel + asp_fused_kernel (every conv / linear layer)",
                          "launches_per_step": g_n.value / args.steps, "ms_per_step_in_kernel": 1000.0 * gemm_s_per_step,
                          "other_kernels_ms_per_step": o_ms.value / args.steps,
                          "algorithmic_gflop_per_utt": algorithmic_flops_per_utt() / 1e9,

@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(384, 1) asp_fused_kernel(const __grid_constant
         uint32_t phase = 0, a_phase = 0;
         int cur_slab = -1;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
-            const int slab = item / p.B, b = item - slab * p.B;
+            const int b = item / slabs, slab = item - b * slabs;  // utterance-major: att / x rows are shared by neighbouring items (L2)
             if (slab != cur_slab) {  // the weight slab stays in shared memory while consecutive items share it
                 mbar_wait(a_empty, a_phase ^ 1u);
                 if (lane == 0) {
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(384, 1) asp_fused_kernel(const __grid_constant
             {  // pull the NEXT item's x tiles (HBM) into L2 while this item is processed
                 const int nitem = item + gridDim.x;
                 if (nitem < items && lane < 2 * ntiles) {
-                    const int nslab = nitem / p.B, nb = nitem - nslab * p.B;
+                    const int nb = nitem / slabs, nslab = nitem - nb * slabs;
                     tma_prefetch_l2_3d(&p.mapX, nslab * 128, nb * p.Tp + p.P + (lane >> 1) * AF_NT, lane & 1);
                 }
                 __syncwarp();
@@ -140,14 +140,14 @@ __global__ void __launch_bounds__(384, 1) asp_fused_kernel(const __grid_constant
         uint32_t phase = 0, acc_phase = 0, a_phase = 0;
         int cur_slab = -1;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
-            const int slab = item / p.B;
+            const int slab = item % slabs;
             if (slab != cur_slab) {
                 mbar_wait(a_full, a_phase);
                 a_phase ^= 1u;
                 cur_slab = slab;
             }
             const int nitem = item + gridDim.x;
-            const bool last_of_slab = (nitem >= items) || (nitem / p.B != slab);
+            const bool last_of_slab = (nitem >= items) || (nitem % slabs != slab);
             for (int ft = 0; ft < ntiles; ++ft) {
                 mbar_wait(tempty(acc), acc_phase ^ 1u);
                 mbar_wait(b_full(stage), phase);
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(384, 1) asp_fused_kernel(const __grid_constant
         int acc = 0, stage = 0;
         uint32_t acc_phase = 0, phase = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
-            const int slab = item / p.B, b = item - slab * p.B;
+            const int b = item / slabs, slab = item - b * slabs;
             const int c = slab * 128 + cl;
             const int64_t goff = int64_t(b) * p.gstat.ld + c;
             const float g = __bfloat162float(p.gstat.hi()[goff]) + __bfloat162float(p.gstat.lo()[goff]);
