@@ -88,6 +88,19 @@ typedef struct {
 } ppv_ecapa_cfg;
 
 void ppv_ecapa_default_cfg(ppv_ecapa_cfg* cfg);
+
+/* kind PPV_MODEL_RESNET_SE: ppvector/models/resnet_se.py:121-139 (SEBottleneck :24-45, SELayer :59-63), ASP head. */
+#define PPV_MODEL_RESNET_SE 2
+typedef struct {
+    int input_size;         /* 80 (must be a multiple of 8) */
+    int embd_dim;           /* 192 */
+    int layers[4];          /* 3,4,6,3 */
+    int num_filters[4];     /* 32,64,128,256 */
+    int attention_channels; /* 128 */
+    int reduction;          /* 8 (SELayer) */
+    int precision;          /* PPV_PREC_* */
+} ppv_resnetse_cfg;
+void ppv_resnetse_default_cfg(ppv_resnetse_cfg* cfg);
 int ppv_model_create(int kind, const void* cfg, ppv_model_t** out);
 int ppv_model_destroy(ppv_model_t* h);
 /* Weights are COPIED (and re-laid-out for the tensor cores) at finalize; names and shapes are the
@@ -107,7 +120,8 @@ int ppv_model_forward(ppv_model_t* h, const float* feat, int B, int T, float* em
 int ppv_model_forward_wav(ppv_model_t* h, ppv_fbank_t* fb, const float* wav, const float* lens_ratio, int B, int L,
                           float* emb, void* ws, size_t ws_bytes, void* stream);
 /* Debug / parity taps: copy an internal activation (valid frames only) to out as fp32.
- * name in {"feat","blocks.0","blocks.1","blocks.2","blocks.3","mfa","asp"}; out is [B,T,C] ([B,C] for asp). */
+ * ECAPA: name in {"feat","blocks.0","blocks.1","blocks.2","blocks.3","mfa","asp"}; out is [B,T,C] ([B,C] for asp).
+ * ResNetSE: {"conv1","layer1".."layer4"} -> [B,H,W,C] (H = frequency, W = time); "flat" -> [B,T',C*H]; "asp" -> [B,2*C*H]. */
 int ppv_model_read_tap(ppv_model_t* h, const char* name, float* out, size_t out_elems, void* stream);
 
 /* Measurement hooks (bench.py): CUDA events around every kernel group of the forward, on the launching stream.

@@ -20,7 +20,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-from oracle import ecapa, fbank, head  # noqa: E402
+from oracle import ecapa, fbank, head, resnet_se  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 REF = "/root/reference"
@@ -74,6 +74,16 @@ def main():
             e[f"tap_{k}_T{T}_absmean"] = np.array(v.abs().mean().item())
     np.savez_compressed(f"{OUT}/ecapa_seed1000.npz", **e)
     print({k: (v.shape, float(np.abs(v).mean())) for k, v in e.items()})
+
+    # ---- ResNetSE embeddings (fp64 oracle)
+    Wr = resnet_se.make_resnet_se_weights(seed=1000, dtype=torch.float64)
+    r = {}
+    for T in (64, 149):
+        gi = torch.Generator().manual_seed(2000 + T)
+        f = torch.randn(2, T, 80, generator=gi, dtype=torch.float64)
+        f = f - f.mean(1, keepdim=True)
+        r[f"emb_T{T}"] = resnet_se.resnet_se_forward(f, Wr).numpy()
+    np.savez_compressed(f"{OUT}/resnetse_seed1000.npz", **r)
 
     # ---- head: AAM + cosine
     g = torch.Generator().manual_seed(1000)

@@ -77,7 +77,7 @@ struct TimeLayout {  // padded time layout of a batch
 // ---- GEMM -----------------------------------------------------------------------------------------
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_MAX_KSTEPS = 64;
+constexpr int GEMM_MAX_KSTEPS = 192;
 constexpr int GEMM_MAX_MAPS = 4;
 
 struct KStep {
@@ -104,6 +104,9 @@ struct Epilogue {
     // row validity: Tp == 0 -> rows [0, M) are all valid (plain matrix); else padded time layout.
     int Tp = 0, P = 0, T = 0;
     int halo = 0;  // also write the reflect halo rows (output feeds a dilated conv)
+    // 2-D image layout (conv2d models): GEMM rows are positions of a zero-bordered [B, img_Hp, img_Wp] grid; a row is
+    // stored iff it is an interior position on the output stride grid, at its position in the [B, out_Hp, out_Wp] grid.
+    int img_Hp = 0, img_Wp = 0, img_H = 0, img_W = 0, img_stride = 1, out_Hp = 0, out_Wp = 0;
     int f32_vec_ok = 0;  // set by gemm_build: OUT_F32 rows are 16-byte (1) / 32-byte (2) aligned
     int tma_store = 0;   // set by gemm_build: planes output without halo goes through a shared-memory staging tile + TMA store
     int debug_nostore = 0;  // PPV_GEMM_NOSTORE=1 (tools/gemm_bench.py only): skip the epilogue stores
@@ -175,9 +178,9 @@ int asp_fused_launch(const AspFusedParams& p, int precision, int num_sms, cudaSt
 // ---- other kernels (elementwise.cu) ---------------------------------------------------------------
 int launch_pack_features(const float* feat, int B, int T, int F, const Planes& out, int P, int Tp, cudaStream_t st);
 int launch_colstats(const Planes& x, int col0, int C, int B, int T, int P, int Tp, int mode, float eps, float* out_f32,
-                    const Planes& out_pl, cudaStream_t st);
+                    const Planes& out_pl, cudaStream_t st, float inv_count = 0.f);
 int launch_se_scale_res(const Planes& z, const float* scale, const Planes& res, int rc0, const Planes& out, int oc0, int C,
-                        int Tp, int64_t rows, int num_sms, cudaStream_t st);
+                        int Tp, int64_t rows, int num_sms, cudaStream_t st, int relu = 0);
 int launch_asp_pool(const float* logits, int64_t lg_ld, const Planes& x, int C, int B, int T, int P, int Tp, float eps,
                     const float* bn_scale, const float* bn_shift, const Planes& out_pl, float* out_raw, cudaStream_t st);
 int launch_planes_to_f32(const Planes& x, int col0, int C, int B, int T, int P, int Tp, float* out, cudaStream_t st);
@@ -206,6 +209,19 @@ int ecapa_forward(EcapaModel* m, const float* feat, Fbank* fb, const float* wav,
 int ecapa_read_tap(EcapaModel* m, const char* name, float* out, size_t out_elems, cudaStream_t st);
 int ecapa_profile(EcapaModel* m, int enable);
 int ecapa_profile_read(EcapaModel* m, double* gemm_ms, double* other_ms, int64_t* gemm_launches, int64_t* other_launches);
+
+// ---- resnet_se.cu -----------------------------------------------------------------------------------
+struct ResNetSEModel;
+void ppv_resnetse_default_cfg_impl(ppv_resnetse_cfg* c);
+int resnetse_create(const ppv_resnetse_cfg* cfg, ResNetSEModel** out);
+void resnetse_destroy(ResNetSEModel* m);
+int resnetse_load_weight(ResNetSEModel* m, const char* name, const float* data, const int64_t* shape, int ndim);
+int resnetse_finalize(ResNetSEModel* m);
+int resnetse_set_precision(ResNetSEModel* m, int precision);
+int resnetse_embd_dim(const ResNetSEModel* m);
+size_t resnetse_workspace_bytes(const ResNetSEModel* m, int B, int T);
+int resnetse_forward(ResNetSEModel* m, const float* feat, int B, int T, float* emb, void* ws, size_t ws_bytes, cudaStream_t st);
+int resnetse_read_tap(ResNetSEModel* m, const char* name, float* out, size_t out_elems, cudaStream_t st);
 
 // ---- cosine.cu / aam.cu -----------------------------------------------------------------------------
 size_t cosine_workspace_bytes(int M, int N, int D);

@@ -87,7 +87,7 @@ __device__ __forceinline__ float2 block_colsum(float2 v, float2 (*s_part)[32], i
 // Single pass with a per-channel shift K = x[first frame]: sum(x-K), sum((x-K)^2); var = (Q - S^2/T)/T.
 // Each lane owns 8 channels (one 16-byte load per plane), 4 frames per warp, 32 frames per block iteration.
 __global__ void __launch_bounds__(STAT_WARPS * 32)
-    colstats_kernel(Planes x, int col0, int C, int T, int P, int Tp, int mode, float eps, float* __restrict__ out_f32,
+    colstats_kernel(Planes x, int col0, int C, int T, int P, int Tp, int mode, float eps, float inv_count, float* __restrict__ out_f32,
                     Planes out_pl) {
     __shared__ float s_s[STAT_WARPS][64];
     __shared__ float s_q[STAT_WARPS][64];
@@ -151,8 +151,8 @@ __global__ void __launch_bounds__(STAT_WARPS * 32)
         // shift of this channel: lane (ch / 8) of warp 0 holds k[ch % 8]; re-read instead of shuffling
         const int64_t off0 = row0 * x.ld + col0 + blockIdx.x * 64 + ch;
         const float K = __bfloat162float(x.hi()[off0]) + __bfloat162float(x.lo()[off0]);
-        const float inv = 1.f / float(T);
-        const float mean = K + S * inv;
+        const float inv = inv_count > 0.f ? inv_count : 1.f / float(T);  // inv_count: zero-bordered images are summed whole
+        const float mean = (inv_count > 0.f ? K * float(T) * inv : K) + S * inv;
         const int cc = blockIdx.x * 64 + ch;
         if (mode == 0) {
             if (out_f32) out_f32[int64_t(b) * C + cc] = mean;
@@ -177,10 +177,10 @@ __global__ void __launch_bounds__(STAT_WARPS * 32)
 }
 
 int launch_colstats(const Planes& x, int col0, int C, int B, int T, int P, int Tp, int mode, float eps, float* out_f32,
-                    const Planes& out_pl, cudaStream_t st) {
+                    const Planes& out_pl, cudaStream_t st, float inv_count) {
     PPV_REQUIRE(C % 64 == 0 && col0 % 8 == 0 && x.ld % 8 == 0, "colstats: C % 64, col0 % 8, ld % 8 required");
     dim3 grid(C / 64, B);
-    PPV_PDL_OK(launch_pdl(colstats_kernel, grid, dim3(STAT_WARPS * 32), 0, st, x, col0, C, T, P, Tp, mode, eps, out_f32, out_pl), "colstats_kernel");
+    PPV_PDL_OK(launch_pdl(colstats_kernel, grid, dim3(STAT_WARPS * 32), 0, st, x, col0, C, T, P, Tp, mode, eps, inv_count, out_f32, out_pl), "colstats_kernel");
     return PPV_OK;
 }
 
@@ -199,7 +199,7 @@ __device__ __forceinline__ void unpack8(const uint4& h, const uint4& l, float (&
 // 8 channels (16 bytes per plane) per thread per iteration
 __global__ void __launch_bounds__(256)
     se_scale_res_kernel(Planes z, const float* __restrict__ scale, Planes res, int rc0, Planes out, int oc0, int C, int Tp,
-                        int64_t rows) {
+                        int64_t rows, int relu) {
     griddep_launch_dependents();
     griddep_wait();
     const int groups = C >> 3;
@@ -219,8 +219,13 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(fmaf(sv[2 * k], zv[2 * k], rv[2 * k]), h0, l0);
-            split_bf16(fmaf(sv[2 * k + 1], zv[2 * k + 1], rv[2 * k + 1]), h1, l1);
+            float y0 = fmaf(sv[2 * k], zv[2 * k], rv[2 * k]), y1 = fmaf(sv[2 * k + 1], zv[2 * k + 1], rv[2 * k + 1]);
+            if (relu) {
+                y0 = fmaxf(y0, 0.f);
+                y1 = fmaxf(y1, 0.f);
+            }
+            split_bf16(y0, h0, l0);
+            split_bf16(y1, h1, l1);
             h[k] = pack_bf16x2(h0, h1);
             l[k] = pack_bf16x2(l0, l1);
         }
@@ -230,12 +235,12 @@ __global__ void __launch_bounds__(256)
 }
 
 int launch_se_scale_res(const Planes& z, const float* scale, const Planes& res, int rc0, const Planes& out, int oc0, int C,
-                        int Tp, int64_t rows, int num_sms, cudaStream_t st) {
+                        int Tp, int64_t rows, int num_sms, cudaStream_t st, int relu) {
     PPV_REQUIRE(C % 8 == 0 && rc0 % 8 == 0 && oc0 % 8 == 0, "se_scale_res: 8-channel alignment required");
     const int64_t total = rows * (C / 8);
     const int64_t want = (total + 255) / 256;
     const int grid = int(std::min<int64_t>(want, int64_t(num_sms) * 16));
-    PPV_PDL_OK(launch_pdl(se_scale_res_kernel, dim3(grid), dim3(256), 0, st, z, scale, res, rc0, out, oc0, C, Tp, rows), "se_scale_res_kernel");
+    PPV_PDL_OK(launch_pdl(se_scale_res_kernel, dim3(grid), dim3(256), 0, st, z, scale, res, rc0, out, oc0, C, Tp, rows, relu), "se_scale_res_kernel");
     return PPV_OK;
 }
 

@@ -76,7 +76,16 @@ __device__ __forceinline__ void epilogue_tile(const Epilogue& ep, const CUtensor
     bool valid = row < M;
     int64_t mirror_a = -1, mirror_b = -1;
     int64_t grp = 0;
-    if (ep.Tp > 0) {
+    int64_t out_row = row;
+    if (ep.img_Wp > 0) {
+        const int64_t img = int64_t(ep.img_Hp) * ep.img_Wp;
+        grp = row / img;
+        const int rem = int(row - grp * img);
+        const int h = rem / ep.img_Wp - 1, w = rem % ep.img_Wp - 1;
+        valid = valid && h >= 0 && h < ep.img_H && w >= 0 && w < ep.img_W;
+        if (ep.img_stride == 2) valid = valid && ((h | w) & 1) == 0;
+        out_row = (grp * ep.out_Hp + h / ep.img_stride + 1) * ep.out_Wp + w / ep.img_stride + 1;
+    } else if (ep.Tp > 0) {
         grp = row / ep.Tp;
         const int t = int(row - grp * ep.Tp) - ep.P;
         valid = valid && t >= 0 && t < ep.T;
@@ -157,7 +166,7 @@ __device__ __forceinline__ void epilogue_tile(const Epilogue& ep, const CUtensor
             for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
         }
         if (ep.out_mode == OUT_F32) {
-            float* dstf = static_cast<float*>(ep.out) + row * ep.out_ld + ep.out_col0 + col;
+            float* dstf = static_cast<float*>(ep.out) + out_row * ep.out_ld + ep.out_col0 + col;
             if (ep.f32_vec_ok == 2 && col + 32 <= N) {  // 32-byte aligned rows: full-sector stores
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
@@ -195,7 +204,7 @@ __device__ __forceinline__ void epilogue_tile(const Epilogue& ep, const CUtensor
                                  l[8 * j + 7]);
                 }
             };
-            store_row(row);
+            store_row(out_row);
             if (mirror_a >= 0) store_row(mirror_a);
             if (mirror_b >= 0) store_row(mirror_b);
         }

@@ -277,7 +277,7 @@ int gemm_build(GemmParams* gp, const GemmSource* srcs, int nsrc, const Planes& W
     int ks = 0;
     for (int i = 0; i < nsrc; ++i) {
         const GemmSource& s = srcs[i];
-        PPV_REQUIRE(s.ncols % 64 == 0 && s.col0 % 8 == 0, "gemm_build: source K slice must be a multiple of 64");
+        PPV_REQUIRE(s.ncols % BK == 0 && s.col0 % 8 == 0, "gemm_build: source K slice must be a multiple of the k-step");
         PPV_REQUIRE(s.col0 + s.ncols <= s.t.ld, "gemm_build: source K slice exceeds the row");
         int mi = -1;
         for (int j = 0; j < nmaps; ++j)
@@ -316,7 +316,7 @@ int gemm_build(GemmParams* gp, const GemmSource* srcs, int nsrc, const Planes& W
         const char* pf = getenv("PPV_GEMM_NO_L2PREFETCH");
         gp->l2_prefetch = (pf && pf[0] == '1') ? 0 : 1;
     }
-    if (epi.out_mode == OUT_PLANES && !epi.halo && (N % 64) == 0) {
+    if (epi.out_mode == OUT_PLANES && !epi.halo && (N % 64) == 0 && epi.img_Wp == 0) {
         const char* nt = getenv("PPV_GEMM_NO_TMASTORE");
         if (!(nt && nt[0] == '1')) {
             Planes po;
