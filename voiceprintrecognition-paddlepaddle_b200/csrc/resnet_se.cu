@@ -247,6 +247,7 @@ int resnetse_finalize(ResNetSEModel* m) {
         }
     }
     m->blocks.clear();
+    m->blocks.reserve(RS_MAX_BLOCKS);  // the arena patches keep pointers into the elements: no reallocation allowed
     int inplanes = cf.num_filters[0];
     for (int li = 1; li <= 4 && ok; ++li) {
         const int planes = cf.num_filters[li - 1], C = 2 * planes, hid = C / cf.reduction;
