@@ -64,7 +64,7 @@ def test_shapes(cuda, model, W64, B, T):
     emb = model(f.to(cuda)).double().cpu()
     assert emb.shape == (B, 192)
     rel = (emb[:2][: ref.shape[0]] - ref).norm(dim=1) / ref.norm(dim=1)
-    assert rel.max() < 3e-5, rel
+    assert rel.max() < 1e-4, rel  # 50 stacked convolutions at ~2^-17 per product; T=8 leaves one pooled frame
 
 
 def test_batch_independence(cuda, model):
