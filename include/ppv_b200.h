@@ -101,6 +101,18 @@ typedef struct {
     int precision;          /* PPV_PREC_* */
 } ppv_resnetse_cfg;
 void ppv_resnetse_default_cfg(ppv_resnetse_cfg* cfg);
+
+/* kind PPV_MODEL_ERES2NET: ppvector/models/eres2net.py:239-263 (blocks :85-108, :147-170, AFF :46-52), TSTP head;
+ * scale 2, expansion 2, base_width 32, one embedding layer (configs/eres2net.yml). */
+#define PPV_MODEL_ERES2NET 3
+typedef struct {
+    int input_size;    /* 80 (must be a multiple of 8) */
+    int embd_dim;      /* 192 */
+    int num_blocks[4]; /* 3,4,6,3 */
+    int m_channels;    /* 32 (or 64) */
+    int precision;     /* PPV_PREC_* */
+} ppv_eres2net_cfg;
+void ppv_eres2net_default_cfg(ppv_eres2net_cfg* cfg);
 int ppv_model_create(int kind, const void* cfg, ppv_model_t** out);
 int ppv_model_destroy(ppv_model_t* h);
 /* Weights are COPIED (and re-laid-out for the tensor cores) at finalize; names and shapes are the
@@ -121,7 +133,8 @@ int ppv_model_forward_wav(ppv_model_t* h, ppv_fbank_t* fb, const float* wav, con
                           float* emb, void* ws, size_t ws_bytes, void* stream);
 /* Debug / parity taps: copy an internal activation (valid frames only) to out as fp32.
  * ECAPA: name in {"feat","blocks.0","blocks.1","blocks.2","blocks.3","mfa","asp"}; out is [B,T,C] ([B,C] for asp).
- * ResNetSE: {"conv1","layer1".."layer4"} -> [B,H,W,C] (H = frequency, W = time); "flat" -> [B,T',C*H]; "asp" -> [B,2*C*H]. */
+ * ResNetSE: {"conv1","layer1".."layer4"} -> [B,H,W,C] (H = frequency, W = time); "flat" -> [B,T',C*H]; "asp" -> [B,2*C*H].
+ * ERes2Net: {"layer1".."layer4","fuse12","fuse123","fuse1234"} -> [B,H,W,C]; "stats" -> [B, 2*C*H]. */
 int ppv_model_read_tap(ppv_model_t* h, const char* name, float* out, size_t out_elems, void* stream);
 
 /* Measurement hooks (bench.py): CUDA events around every kernel group of the forward, on the launching stream.

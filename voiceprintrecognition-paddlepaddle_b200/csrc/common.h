@@ -96,6 +96,8 @@ struct Epilogue {
     int relu = 0;
     int tanh_ = 0;
     int sigmoid_ = 0;
+    int silu_ = 0;
+    float relu_max = 0.f;  // > 0: clipped ReLU (Hardtanh(0, relu_max), ERes2Net) applied where `relu` is set
     int out_mode = OUT_PLANES;
     void* out = nullptr;            // Planes base (bf16) or float*
     int64_t out_ld = 0;             // elements
@@ -180,7 +182,7 @@ int launch_pack_features(const float* feat, int B, int T, int F, const Planes& o
 int launch_colstats(const Planes& x, int col0, int C, int B, int T, int P, int Tp, int mode, float eps, float* out_f32,
                     const Planes& out_pl, cudaStream_t st, float inv_count = 0.f);
 int launch_se_scale_res(const Planes& z, const float* scale, const Planes& res, int rc0, const Planes& out, int oc0, int C,
-                        int Tp, int64_t rows, int num_sms, cudaStream_t st, int relu = 0);
+                        int Tp, int64_t rows, int num_sms, cudaStream_t st, int relu = 0, float relu_max = 0.f);
 int launch_asp_pool(const float* logits, int64_t lg_ld, const Planes& x, int C, int B, int T, int P, int Tp, float eps,
                     const float* bn_scale, const float* bn_shift, const Planes& out_pl, float* out_raw, cudaStream_t st);
 int launch_planes_to_f32(const Planes& x, int col0, int C, int B, int T, int P, int Tp, float* out, cudaStream_t st);
@@ -210,6 +212,21 @@ int ecapa_read_tap(EcapaModel* m, const char* name, float* out, size_t out_elems
 int ecapa_profile(EcapaModel* m, int enable);
 int ecapa_profile_read(EcapaModel* m, double* gemm_ms, double* other_ms, int64_t* gemm_launches, int64_t* other_launches);
 
+// ---- conv2d models: zero-bordered NHWC image grids (resnet_se.cu, eres2net.cu) ------------------------
+struct ImageGeo {
+    int H = 0, W = 0, Hp = 0, Wp = 0;
+    int64_t rows(int B) const { return int64_t(B) * Hp * Wp; }
+};
+// stem: 1 -> C0 channels, 3x3, padding 1, folded BN, ReLU, from feats [B,T,F] (image = feats transposed: H = F, W = T)
+int launch_stem_conv(const float* feat, int B, int T, int F, const float* w9, const float* bias, int C0, const Planes& out, int Hp, int Wp,
+                     cudaStream_t st);
+// [B,Hp,Wp,C] image -> [B*W, C*H] time-major matrix (channel index c*H + h)
+int launch_flatten_image(const Planes& in, int B, int H, int W, int Hp, int Wp, int C, const Planes& out, int num_sms, cudaStream_t st);
+int launch_image_to_f32(const Planes& in, int B, int H, int W, int Hp, int Wp, int C, float* out, cudaStream_t st);
+// xo = x * (1 + t) + y * (1 - t)  (AFF blend, eres2net.py:50-51 with t = tanh(att)); all rows
+int launch_aff_combine(const Planes& x, int xc0, const Planes& y, int yc0, const Planes& t, const Planes& out, int C, int64_t rows, int num_sms,
+                       cudaStream_t st);
+
 // ---- resnet_se.cu -----------------------------------------------------------------------------------
 struct ResNetSEModel;
 void ppv_resnetse_default_cfg_impl(ppv_resnetse_cfg* c);
@@ -222,6 +239,19 @@ int resnetse_embd_dim(const ResNetSEModel* m);
 size_t resnetse_workspace_bytes(const ResNetSEModel* m, int B, int T);
 int resnetse_forward(ResNetSEModel* m, const float* feat, int B, int T, float* emb, void* ws, size_t ws_bytes, cudaStream_t st);
 int resnetse_read_tap(ResNetSEModel* m, const char* name, float* out, size_t out_elems, cudaStream_t st);
+
+// ---- eres2net.cu ------------------------------------------------------------------------------------
+struct ERes2NetModel;
+void ppv_eres2net_default_cfg_impl(ppv_eres2net_cfg* c);
+int eres2net_create(const ppv_eres2net_cfg* cfg, ERes2NetModel** out);
+void eres2net_destroy(ERes2NetModel* m);
+int eres2net_load_weight(ERes2NetModel* m, const char* name, const float* data, const int64_t* shape, int ndim);
+int eres2net_finalize(ERes2NetModel* m);
+int eres2net_set_precision(ERes2NetModel* m, int precision);
+int eres2net_embd_dim(const ERes2NetModel* m);
+size_t eres2net_workspace_bytes(const ERes2NetModel* m, int B, int T);
+int eres2net_forward(ERes2NetModel* m, const float* feat, int B, int T, float* emb, void* ws, size_t ws_bytes, cudaStream_t st);
+int eres2net_read_tap(ERes2NetModel* m, const char* name, float* out, size_t out_elems, cudaStream_t st);
 
 // ---- cosine.cu / aam.cu -----------------------------------------------------------------------------
 size_t cosine_workspace_bytes(int M, int N, int D);

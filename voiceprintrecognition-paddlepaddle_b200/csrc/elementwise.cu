@@ -84,6 +84,7 @@ __device__ __forceinline__ float2 block_colsum(float2 v, float2 (*s_part)[32], i
 
 // mode 0: mean -> out_f32[b, C] and/or planes [B, C]                                  (SE squeeze)
 // mode 1: mean and std = sqrt(clip(var, eps)) -> planes [B, 2C] (mean | std)             (ASP global context)
+// mode 2: mean and std = sqrt(var_unbiased + eps) -> planes [B, 2C]                       (TSTP, pooling.py:138-146)
 // Single pass with a per-channel shift K = x[first frame]: sum(x-K), sum((x-K)^2); var = (Q - S^2/T)/T.
 // Each lane owns 8 channels (one 16-byte load per plane), 4 frames per warp, 32 frames per block iteration.
 __global__ void __launch_bounds__(STAT_WARPS * 32)
@@ -163,8 +164,9 @@ __global__ void __launch_bounds__(STAT_WARPS * 32)
                 out_pl.lo()[int64_t(b) * out_pl.ld + cc] = l;
             }
         } else {
-            const float var = (Q - S * S * inv) * inv;
-            const float sd = sqrtf(fmaxf(var, eps));
+            // mode 1: ASP global std = sqrt(clip(var_biased, eps)); mode 2: TSTP std = sqrt(var_unbiased + eps)
+            const float ssq = Q - S * S * inv;
+            const float sd = (mode == 2) ? sqrtf(fmaxf(ssq, 0.f) / float(T > 1 ? T - 1 : 1) + eps) : sqrtf(fmaxf(ssq * inv, eps));
             __nv_bfloat16 h, l;
             split_bf16(mean, h, l);
             out_pl.hi()[int64_t(b) * out_pl.ld + cc] = h;
@@ -199,7 +201,7 @@ __device__ __forceinline__ void unpack8(const uint4& h, const uint4& l, float (&
 // 8 channels (16 bytes per plane) per thread per iteration
 __global__ void __launch_bounds__(256)
     se_scale_res_kernel(Planes z, const float* __restrict__ scale, Planes res, int rc0, Planes out, int oc0, int C, int Tp,
-                        int64_t rows, int relu) {
+                        int64_t rows, int relu, float relu_max) {
     griddep_launch_dependents();
     griddep_wait();
     const int groups = C >> 3;
@@ -212,8 +214,11 @@ __global__ void __launch_bounds__(256)
         unpack8(*reinterpret_cast<const uint4*>(z.hi() + r * z.ld + c), *reinterpret_cast<const uint4*>(z.lo() + r * z.ld + c), zv);
         unpack8(*reinterpret_cast<const uint4*>(res.hi() + r * res.ld + rc0 + c),
                 *reinterpret_cast<const uint4*>(res.lo() + r * res.ld + rc0 + c), rv);
-        const float4 s0 = *reinterpret_cast<const float4*>(scale + int64_t(b) * C + c);
-        const float4 s1 = *reinterpret_cast<const float4*>(scale + int64_t(b) * C + c + 4);
+        float4 s0 = make_float4(1.f, 1.f, 1.f, 1.f), s1 = s0;  // scale == nullptr: plain residual add
+        if (scale) {
+            s0 = *reinterpret_cast<const float4*>(scale + int64_t(b) * C + c);
+            s1 = *reinterpret_cast<const float4*>(scale + int64_t(b) * C + c + 4);
+        }
         const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
         uint32_t h[4], l[4];
 #pragma unroll
@@ -223,6 +228,10 @@ __global__ void __launch_bounds__(256)
             if (relu) {
                 y0 = fmaxf(y0, 0.f);
                 y1 = fmaxf(y1, 0.f);
+                if (relu_max > 0.f) {
+                    y0 = fminf(y0, relu_max);
+                    y1 = fminf(y1, relu_max);
+                }
             }
             split_bf16(y0, h0, l0);
             split_bf16(y1, h1, l1);
@@ -235,12 +244,12 @@ __global__ void __launch_bounds__(256)
 }
 
 int launch_se_scale_res(const Planes& z, const float* scale, const Planes& res, int rc0, const Planes& out, int oc0, int C,
-                        int Tp, int64_t rows, int num_sms, cudaStream_t st, int relu) {
+                        int Tp, int64_t rows, int num_sms, cudaStream_t st, int relu, float relu_max) {
     PPV_REQUIRE(C % 8 == 0 && rc0 % 8 == 0 && oc0 % 8 == 0, "se_scale_res: 8-channel alignment required");
     const int64_t total = rows * (C / 8);
     const int64_t want = (total + 255) / 256;
     const int grid = int(std::min<int64_t>(want, int64_t(num_sms) * 16));
-    PPV_PDL_OK(launch_pdl(se_scale_res_kernel, dim3(grid), dim3(256), 0, st, z, scale, res, rc0, out, oc0, C, Tp, rows, relu), "se_scale_res_kernel");
+    PPV_PDL_OK(launch_pdl(se_scale_res_kernel, dim3(grid), dim3(256), 0, st, z, scale, res, rc0, out, oc0, C, Tp, rows, relu, relu_max), "se_scale_res_kernel");
     return PPV_OK;
 }
 
@@ -322,6 +331,43 @@ int launch_asp_pool(const float* logits, int64_t lg_ld, const Planes& x, int C, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// AFF blend: xo = x * (1 + t) + y * (1 - t), 8 channels per thread
+__global__ void __launch_bounds__(256)
+    aff_combine_kernel(Planes x, int xc0, Planes y, int yc0, Planes t, Planes out, int C, int64_t rows) {
+    griddep_launch_dependents();
+    griddep_wait();
+    const int groups = C >> 3;
+    const int64_t total = rows * groups;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t r = i / groups;
+        const int c = int(i - r * groups) * 8;
+        float xv[8], yv[8], tv[8];
+        unpack8(*reinterpret_cast<const uint4*>(x.hi() + r * x.ld + xc0 + c), *reinterpret_cast<const uint4*>(x.lo() + r * x.ld + xc0 + c), xv);
+        unpack8(*reinterpret_cast<const uint4*>(y.hi() + r * y.ld + yc0 + c), *reinterpret_cast<const uint4*>(y.lo() + r * y.ld + yc0 + c), yv);
+        unpack8(*reinterpret_cast<const uint4*>(t.hi() + r * t.ld + c), *reinterpret_cast<const uint4*>(t.lo() + r * t.ld + c), tv);
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(fmaf(xv[2 * k], 1.f + tv[2 * k], yv[2 * k] * (1.f - tv[2 * k])), h0, l0);
+            split_bf16(fmaf(xv[2 * k + 1], 1.f + tv[2 * k + 1], yv[2 * k + 1] * (1.f - tv[2 * k + 1])), h1, l1);
+            h[k] = pack_bf16x2(h0, h1);
+            l[k] = pack_bf16x2(l0, l1);
+        }
+        *reinterpret_cast<uint4*>(out.hi() + r * out.ld + c) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(out.lo() + r * out.ld + c) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+
+int launch_aff_combine(const Planes& x, int xc0, const Planes& y, int yc0, const Planes& t, const Planes& out, int C, int64_t rows, int num_sms,
+                       cudaStream_t st) {
+    PPV_REQUIRE(C % 8 == 0 && xc0 % 8 == 0 && yc0 % 8 == 0, "aff_combine: 8-channel alignment required");
+    const int64_t total = rows * (C / 8);
+    const int grid = int(std::min<int64_t>((total + 255) / 256, int64_t(num_sms) * 16));
+    PPV_PDL_OK(launch_pdl(aff_combine_kernel, dim3(grid), dim3(256), 0, st, x, xc0, y, yc0, t, out, C, rows), "aff_combine_kernel");
+    return PPV_OK;
+}
+
 // planes (padded layout, valid frames) -> fp32 [B,T,C]   (debug taps / tests)
 __global__ void planes_to_f32_kernel(Planes x, int col0, int C, int B, int T, int P, int Tp, float* __restrict__ out) {
     const int64_t total = int64_t(B) * T * C;

@@ -42,6 +42,14 @@ __device__ __forceinline__ void epilogue_math(const Epilogue& ep, int N, int col
     if (ep.relu) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+        if (ep.relu_max > 0.f) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = fminf(x[j], ep.relu_max);
+        }
+    }
+    if (ep.silu_) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = x[j] / (1.f + expf(-x[j]));
     }
     if (ep.bn_scale) {
         const float4* sc = reinterpret_cast<const float4*>(ep.bn_scale + col);

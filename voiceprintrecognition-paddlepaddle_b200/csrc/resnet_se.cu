@@ -25,10 +25,7 @@ namespace {
 
 constexpr int RS_MAX_BLOCKS = 32;
 
-struct Geo {  // one zero-bordered image grid
-    int H = 0, W = 0, Hp = 0, Wp = 0;
-    int64_t rows(int B) const { return int64_t(B) * Hp * Wp; }
-};
+using Geo = ImageGeo;  // one zero-bordered image grid
 
 struct BlockW {
     GemmWeights conv1, conv2, conv3, down, se1, se2;
@@ -142,6 +139,26 @@ __global__ void rs_image_to_f32_kernel(Planes in, int B, int H, int W, int Hp, i
         const int64_t src = ((int64_t(b) * Hp + h + 1) * Wp + w + 1) * in.ld + c;
         out[i] = __bfloat162float(in.hi()[src]) + __bfloat162float(in.lo()[src]);
     }
+}
+
+int launch_stem_conv(const float* feat, int B, int T, int F, const float* w9, const float* bias, int C0, const Planes& out, int Hp, int Wp,
+                     cudaStream_t st) {
+    const int64_t total = int64_t(B) * F * T;
+    PPV_PDL_OK(launch_pdl(rs_conv1_kernel, dim3(unsigned((total + 7) / 8)), dim3(256), 0, st, feat, B, T, F, w9, bias, C0, out, Hp, Wp),
+               "rs_conv1_kernel");
+    return PPV_OK;
+}
+int launch_flatten_image(const Planes& in, int B, int H, int W, int Hp, int Wp, int C, const Planes& out, int num_sms, cudaStream_t st) {
+    const int64_t total = int64_t(B) * W * C * H;
+    const int grid = int(std::min<int64_t>((total + 255) / 256, int64_t(num_sms) * 16));
+    PPV_PDL_OK(launch_pdl(rs_flatten_kernel, dim3(grid), dim3(256), 0, st, in, B, H, W, Hp, Wp, C, out), "rs_flatten_kernel");
+    return PPV_OK;
+}
+int launch_image_to_f32(const Planes& in, int B, int H, int W, int Hp, int Wp, int C, float* out, cudaStream_t st) {
+    const int64_t total = int64_t(B) * H * W * C;
+    rs_image_to_f32_kernel<<<int(std::min<int64_t>((total + 255) / 256, 148 * 32)), 256, 0, st>>>(in, B, H, W, Hp, Wp, C, out);
+    PPV_LAUNCH_OK("rs_image_to_f32_kernel");
+    return PPV_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ create / load

@@ -36,6 +36,14 @@ class ResNetSECfg(C.Structure):
 
 
 PPV_MODEL_RESNET_SE = 2
+PPV_MODEL_ERES2NET = 3
+
+
+class ERes2NetCfg(C.Structure):
+    _fields_ = [("input_size", C.c_int), ("embd_dim", C.c_int), ("num_blocks", C.c_int * 4), ("m_channels", C.c_int),
+                ("precision", C.c_int)]
+
+
 _P = C.c_void_p
 # name -> (restype, argtypes); this table is also what tests/test_abi.py checks against include/ppv_b200.h
 SIGNATURES = {
@@ -50,6 +58,7 @@ SIGNATURES = {
     "ppv_fbank_forward": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P]),
     "ppv_ecapa_default_cfg": (None, [C.POINTER(EcapaCfg)]),
     "ppv_resnetse_default_cfg": (None, [C.POINTER(ResNetSECfg)]),
+    "ppv_eres2net_default_cfg": (None, [C.POINTER(ERes2NetCfg)]),
     "ppv_model_create": (C.c_int, [C.c_int, _P, C.POINTER(_P)]),
     "ppv_model_destroy": (C.c_int, [_P]),
     "ppv_model_load_weight": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int]),
