@@ -113,6 +113,19 @@ typedef struct {
     int precision;     /* PPV_PREC_* */
 } ppv_eres2net_cfg;
 void ppv_eres2net_default_cfg(ppv_eres2net_cfg* cfg);
+
+/* kind PPV_MODEL_CAMPPLUS: ppvector/models/campplus.py:292-346 (FCM head :254-289, CAM dense TDNN layers :67-141,
+ * transit :174-186, statistics pooling :24-31, dense :189-204); blocks 12/24/16, dilations 1/2/2 (configs/cam++.yml). */
+#define PPV_MODEL_CAMPPLUS 4
+typedef struct {
+    int input_size;    /* 80 (must be a multiple of 8) */
+    int embd_dim;      /* 192 */
+    int growth_rate;   /* 32 */
+    int bn_size;       /* 4 */
+    int init_channels; /* 128 */
+    int precision;     /* PPV_PREC_* */
+} ppv_campplus_cfg;
+void ppv_campplus_default_cfg(ppv_campplus_cfg* cfg);
 int ppv_model_create(int kind, const void* cfg, ppv_model_t** out);
 int ppv_model_destroy(ppv_model_t* h);
 /* Weights are COPIED (and re-laid-out for the tensor cores) at finalize; names and shapes are the

@@ -20,7 +20,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-from oracle import ecapa, eres2net, fbank, head, resnet_se  # noqa: E402
+from oracle import campplus, ecapa, eres2net, fbank, head, resnet_se  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 REF = "/root/reference"
@@ -94,6 +94,16 @@ def main():
         f = f - f.mean(1, keepdim=True)
         r[f"emb_T{T}"] = eres2net.eres2net_forward(f, We).numpy()
     np.savez_compressed(f"{OUT}/eres2net_seed1000.npz", **r)
+
+    # ---- CAM++ embeddings (fp64 oracle)
+    Wc_ = campplus.make_campplus_weights(seed=1000, dtype=torch.float64)
+    r = {}
+    for T in (64, 298, 451):
+        gi = torch.Generator().manual_seed(4000 + T)
+        f = torch.randn(2, T, 80, generator=gi, dtype=torch.float64)
+        f = f - f.mean(1, keepdim=True)
+        r[f"emb_T{T}"] = campplus.campplus_forward(f, Wc_).numpy()
+    np.savez_compressed(f"{OUT}/campplus_seed1000.npz", **r)
 
     # ---- head: AAM + cosine
     g = torch.Generator().manual_seed(1000)

@@ -74,3 +74,44 @@ def test_margin_scheduler():
     assert 0.0 < mid < 0.3
     expect = 0.3 * (1.0 - math.exp(0.5 * math.log(1e-3 / (1.0 + 1e-6))))
     assert abs(mid - expect) < 1e-12
+
+
+# ------------------------------------------------------------------------------------------------ CAM++
+def test_campplus_param_count_and_golden(golden_dir):
+    from oracle import campplus
+    W = campplus.make_campplus_weights(seed=1000, dtype=torch.float32)
+    assert campplus.count_params(W) == 6859232  # README.md:72 "CAM++ 6.8 M"
+    g = np.load(f"{golden_dir}/campplus_seed1000.npz")
+    gi = torch.Generator().manual_seed(4000 + 64)
+    f = torch.randn(2, 64, 80, generator=gi, dtype=torch.float64)
+    f = (f - f.mean(1, keepdim=True)).float()
+    emb = campplus.campplus_forward(f, W).double().numpy()
+    assert np.abs(emb - g["emb_T64"]).max() < 2e-5
+
+
+@pytest.mark.parametrize("T", [1, 99, 100, 101, 149, 250])
+def test_campplus_seg_pooling_is_ceil_mode_avg_pool(T):
+    # campplus.py:95-106: avg_pool1d(kernel 100, stride 100, ceil_mode=True), expand each segment value over 100 frames, crop to T
+    from oracle import campplus
+    x = torch.randn(2, 5, T, dtype=torch.float64)
+    seg = torch.nn.functional.avg_pool1d(x, kernel_size=100, stride=100, ceil_mode=True)
+    want = seg.unsqueeze(-1).expand(*seg.shape, 100).reshape(*seg.shape[:-1], -1)[..., :T]
+    assert torch.allclose(campplus.seg_pooling(x), want, atol=1e-12)
+
+
+def test_campplus_tdnn_frame_pair_identity():
+    # the stride-2 k5 conv over frames equals five taps over (even | odd) frame pairs at offsets -1,-1,0,0,+1 (csrc/campplus.cu)
+    g = torch.Generator().manual_seed(5)
+    for T in (7, 8):
+        x = torch.randn(1, 3, T, generator=g, dtype=torch.float64)
+        w = torch.randn(4, 3, 5, generator=g, dtype=torch.float64)
+        want = torch.nn.functional.conv1d(x, w, stride=2, padding=2)
+        T2 = (T - 1) // 2 + 1
+        ev = torch.zeros(1, 3, T2 + 2, dtype=torch.float64)
+        od = torch.zeros(1, 3, T2 + 2, dtype=torch.float64)
+        ev[..., 1:1 + (T + 1) // 2] = x[..., 0::2]
+        od[..., 1:1 + T // 2] = x[..., 1::2]
+        got = torch.zeros_like(want)
+        for k, (src, off) in enumerate([(ev, -1), (od, -1), (ev, 0), (od, 0), (ev, 1)]):
+            got += torch.einsum("oc,bct->bot", w[:, :, k], src[..., 1 + off:1 + off + T2])
+        assert torch.allclose(got, want, atol=1e-12)

@@ -47,6 +47,7 @@ struct ppv_model {
     EcapaModel* ecapa;
     ResNetSEModel* resnet;
     ERes2NetModel* eres;
+    CamppModel* campp;
 };
 
 #define PPV_GUARD_BEGIN try {
@@ -135,6 +136,9 @@ void ppv_ecapa_default_cfg(ppv_ecapa_cfg* c) {
 void ppv_eres2net_default_cfg(ppv_eres2net_cfg* c) {
     if (c) ppv_eres2net_default_cfg_impl(c);
 }
+void ppv_campplus_default_cfg(ppv_campplus_cfg* c) {
+    if (c) ppv_campplus_default_cfg_impl(c);
+}
 void ppv_resnetse_default_cfg(ppv_resnetse_cfg* c) {
     if (c) ppv_resnetse_default_cfg_impl(c);
 }
@@ -142,28 +146,36 @@ void ppv_resnetse_default_cfg(ppv_resnetse_cfg* c) {
 int ppv_model_create(int kind, const void* cfg, ppv_model_t** out) {
     PPV_GUARD_BEGIN
     PPV_REQUIRE(cfg && out, "ppv_model_create: null argument");
-    if (kind != PPV_MODEL_ECAPA_TDNN && kind != PPV_MODEL_RESNET_SE && kind != PPV_MODEL_ERES2NET)
-        return fail(PPV_EUNSUPPORTED, "ppv_model_create: implemented kinds are PPV_MODEL_ECAPA_TDNN, PPV_MODEL_RESNET_SE, PPV_MODEL_ERES2NET");
+    if (kind != PPV_MODEL_ECAPA_TDNN && kind != PPV_MODEL_RESNET_SE && kind != PPV_MODEL_ERES2NET && kind != PPV_MODEL_CAMPPLUS)
+        return fail(PPV_EUNSUPPORTED,
+                    "ppv_model_create: implemented kinds are PPV_MODEL_ECAPA_TDNN, PPV_MODEL_RESNET_SE, PPV_MODEL_ERES2NET, PPV_MODEL_CAMPPLUS");
     int rc = check_device();
     if (rc) return rc;
     if (kind == PPV_MODEL_RESNET_SE) {
         ResNetSEModel* r = nullptr;
         rc = resnetse_create(static_cast<const ppv_resnetse_cfg*>(cfg), &r);
         if (rc) return rc;
-        *out = new ppv_model{kind, nullptr, r, nullptr};
+        *out = new ppv_model{kind, nullptr, r, nullptr, nullptr};
         return PPV_OK;
     }
     if (kind == PPV_MODEL_ERES2NET) {
         ERes2NetModel* e = nullptr;
         rc = eres2net_create(static_cast<const ppv_eres2net_cfg*>(cfg), &e);
         if (rc) return rc;
-        *out = new ppv_model{kind, nullptr, nullptr, e};
+        *out = new ppv_model{kind, nullptr, nullptr, e, nullptr};
+        return PPV_OK;
+    }
+    if (kind == PPV_MODEL_CAMPPLUS) {
+        CamppModel* c = nullptr;
+        rc = campplus_create(static_cast<const ppv_campplus_cfg*>(cfg), &c);
+        if (rc) return rc;
+        *out = new ppv_model{kind, nullptr, nullptr, nullptr, c};
         return PPV_OK;
     }
     EcapaModel* m = nullptr;
     rc = ecapa_create(static_cast<const ppv_ecapa_cfg*>(cfg), &m);
     if (rc) return rc;
-    *out = new ppv_model{kind, m, nullptr, nullptr};
+    *out = new ppv_model{kind, m, nullptr, nullptr, nullptr};
     return PPV_OK;
     PPV_GUARD_END
 }
@@ -172,6 +184,7 @@ int ppv_model_destroy(ppv_model_t* h) {
     ecapa_destroy(h->ecapa);
     resnetse_destroy(h->resnet);
     eres2net_destroy(h->eres);
+    campplus_destroy(h->campp);
     delete h;
     return PPV_OK;
 }
@@ -180,6 +193,7 @@ int ppv_model_load_weight(ppv_model_t* h, const char* name, const float* data, c
     PPV_REQUIRE(h, "ppv_model_load_weight: null model");
     if (h->resnet) return resnetse_load_weight(h->resnet, name, data, shape, ndim);
     if (h->eres) return eres2net_load_weight(h->eres, name, data, shape, ndim);
+    if (h->campp) return campplus_load_weight(h->campp, name, data, shape, ndim);
     return ecapa_load_weight(h->ecapa, name, data, shape, ndim);
     PPV_GUARD_END
 }
@@ -188,6 +202,7 @@ int ppv_model_finalize(ppv_model_t* h) {
     PPV_REQUIRE(h, "ppv_model_finalize: null model");
     if (h->resnet) return resnetse_finalize(h->resnet);
     if (h->eres) return eres2net_finalize(h->eres);
+    if (h->campp) return campplus_finalize(h->campp);
     return ecapa_finalize(h->ecapa);
     PPV_GUARD_END
 }
@@ -195,12 +210,16 @@ int ppv_model_set_precision(ppv_model_t* h, int precision) {
     PPV_REQUIRE(h, "ppv_model_set_precision: null model");
     if (h->resnet) return resnetse_set_precision(h->resnet, precision);
     if (h->eres) return eres2net_set_precision(h->eres, precision);
+    if (h->campp) return campplus_set_precision(h->campp, precision);
     return ecapa_set_precision(h->ecapa, precision);
 }
 int ppv_model_embd_dim(const ppv_model_t* h) {
-    return !h ? 0 : h->resnet ? resnetse_embd_dim(h->resnet) : h->eres ? eres2net_embd_dim(h->eres) : ecapa_embd_dim(h->ecapa);
+    if (!h) return 0;
+    if (h->campp) return campplus_embd_dim(h->campp);
+    return h->resnet ? resnetse_embd_dim(h->resnet) : h->eres ? eres2net_embd_dim(h->eres) : ecapa_embd_dim(h->ecapa);
 }
 size_t ppv_model_workspace_bytes(const ppv_model_t* h, int B, int T) {
+    if (h && h->campp) return campplus_workspace_bytes(h->campp, B, T);
     return !h ? 0 : h->resnet ? resnetse_workspace_bytes(h->resnet, B, T) : h->eres ? eres2net_workspace_bytes(h->eres, B, T)
                                                                               : ecapa_workspace_bytes(h->ecapa, B, T);
 }
@@ -210,6 +229,7 @@ int ppv_model_forward(ppv_model_t* h, const float* feat, int B, int T, float* em
     PPV_REQUIRE(h && feat && emb, "ppv_model_forward: null argument");
     if (h->resnet) return resnetse_forward(h->resnet, feat, B, T, emb, ws, ws_bytes, static_cast<cudaStream_t>(stream));
     if (h->eres) return eres2net_forward(h->eres, feat, B, T, emb, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+    if (h->campp) return campplus_forward(h->campp, feat, B, T, emb, ws, ws_bytes, static_cast<cudaStream_t>(stream));
     return ecapa_forward(h->ecapa, feat, nullptr, nullptr, nullptr, B, T, 0, emb, ws, ws_bytes, static_cast<cudaStream_t>(stream));
     PPV_GUARD_END
 }
@@ -217,7 +237,7 @@ int ppv_model_forward_wav(ppv_model_t* h, ppv_fbank_t* fb, const float* wav, con
                           void* ws, size_t ws_bytes, void* stream) {
     PPV_GUARD_BEGIN
     PPV_REQUIRE(h && fb && wav && emb, "ppv_model_forward_wav: null argument");
-    if (h->resnet || h->eres) return fail(PPV_EUNSUPPORTED, "ppv_model_forward_wav: the fused waveform path exists for ECAPA-TDNN only; call ppv_fbank_forward + ppv_model_forward");
+    if (h->resnet || h->eres || h->campp) return fail(PPV_EUNSUPPORTED, "ppv_model_forward_wav: the fused waveform path exists for ECAPA-TDNN only; call ppv_fbank_forward + ppv_model_forward");
     const int T = fbank_num_frames(fb->impl, L);
     PPV_REQUIRE(T > 0, "ppv_model_forward_wav: waveform shorter than one frame");
     return ecapa_forward(h->ecapa, nullptr, fb->impl, wav, lens_ratio, B, T, L, emb, ws, ws_bytes, static_cast<cudaStream_t>(stream));
@@ -228,6 +248,7 @@ int ppv_model_read_tap(ppv_model_t* h, const char* name, float* out, size_t out_
     PPV_REQUIRE(h, "ppv_model_read_tap: null model");
     if (h->resnet) return resnetse_read_tap(h->resnet, name, out, out_elems, static_cast<cudaStream_t>(stream));
     if (h->eres) return eres2net_read_tap(h->eres, name, out, out_elems, static_cast<cudaStream_t>(stream));
+    if (h->campp) return campplus_read_tap(h->campp, name, out, out_elems, static_cast<cudaStream_t>(stream));
     return ecapa_read_tap(h->ecapa, name, out, out_elems, static_cast<cudaStream_t>(stream));
     PPV_GUARD_END
 }

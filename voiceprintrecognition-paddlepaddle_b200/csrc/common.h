@@ -109,6 +109,12 @@ struct Epilogue {
     // 2-D image layout (conv2d models): GEMM rows are positions of a zero-bordered [B, img_Hp, img_Wp] grid; a row is
     // stored iff it is an interior position on the output stride grid, at its position in the [B, out_Hp, out_Wp] grid.
     int img_Hp = 0, img_Wp = 0, img_H = 0, img_W = 0, img_stride = 1, out_Hp = 0, out_Wp = 0;
+    int img_stride_w = 0;  // 0: same as img_stride; CAM++'s FCM strides the frequency axis only (campplus.py:223-224)
+    // per-(utterance, time segment) output scale, padded time layout only: y *= seg_scale[(b * nseg + t / seg_len) * N + n]
+    // (context-aware mask of CAM++, campplus.py:88-93); applied after the biases, before the activations
+    const float* seg_scale = nullptr;
+    int seg_len = 0, nseg = 0;
+    int zero_invalid = 0;  // TMA-store path: rows outside the valid frames are stored as zeros (zero-padded convs read them)
     int f32_vec_ok = 0;  // set by gemm_build: OUT_F32 rows are 16-byte (1) / 32-byte (2) aligned
     int tma_store = 0;   // set by gemm_build: planes output without halo goes through a shared-memory staging tile + TMA store
     int debug_nostore = 0;  // PPV_GEMM_NOSTORE=1 (tools/gemm_bench.py only): skip the epilogue stores
@@ -252,6 +258,19 @@ int eres2net_embd_dim(const ERes2NetModel* m);
 size_t eres2net_workspace_bytes(const ERes2NetModel* m, int B, int T);
 int eres2net_forward(ERes2NetModel* m, const float* feat, int B, int T, float* emb, void* ws, size_t ws_bytes, cudaStream_t st);
 int eres2net_read_tap(ERes2NetModel* m, const char* name, float* out, size_t out_elems, cudaStream_t st);
+
+// ---- campplus.cu ------------------------------------------------------------------------------------
+struct CamppModel;
+void ppv_campplus_default_cfg_impl(ppv_campplus_cfg* c);
+int campplus_create(const ppv_campplus_cfg* cfg, CamppModel** out);
+void campplus_destroy(CamppModel* m);
+int campplus_load_weight(CamppModel* m, const char* name, const float* data, const int64_t* shape, int ndim);
+int campplus_finalize(CamppModel* m);
+int campplus_set_precision(CamppModel* m, int precision);
+int campplus_embd_dim(const CamppModel* m);
+size_t campplus_workspace_bytes(const CamppModel* m, int B, int T);
+int campplus_forward(CamppModel* m, const float* feat, int B, int T, float* emb, void* ws, size_t ws_bytes, cudaStream_t st);
+int campplus_read_tap(CamppModel* m, const char* name, float* out, size_t out_elems, cudaStream_t st);
 
 // ---- cosine.cu / aam.cu -----------------------------------------------------------------------------
 size_t cosine_workspace_bytes(int M, int N, int D);

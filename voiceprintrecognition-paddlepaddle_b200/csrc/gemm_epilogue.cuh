@@ -14,7 +14,8 @@ constexpr int GEMM_THREADS = 128 + GEMM_EPI_THREADS;  // + TMA, MMA, TMEM-alloc,
 constexpr int EPI_STAGING_BYTES = 2 * GEMM_BM * 128;  // [hi | lo] x 128 rows x 64 bf16 columns, SWIZZLE_128B
 
 // per-column epilogue math on 32 accumulator columns starting at global column `col`
-__device__ __forceinline__ void epilogue_math(const Epilogue& ep, int N, int col, int64_t grp, const uint32_t (&v)[32], float (&x)[32]) {
+__device__ __forceinline__ void epilogue_math(const Epilogue& ep, int N, int col, int64_t grp, int64_t sgrp, const uint32_t (&v)[32],
+                                              float (&x)[32]) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
     if (ep.bias) {
@@ -37,6 +38,17 @@ __device__ __forceinline__ void epilogue_math(const Epilogue& ep, int N, int col
             x[4 * j + 1] += b4.y;
             x[4 * j + 2] += b4.z;
             x[4 * j + 3] += b4.w;
+        }
+    }
+    if (ep.seg_scale) {
+        const float4* sg = reinterpret_cast<const float4*>(ep.seg_scale + sgrp * N + col);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 s4 = __ldg(sg + j);
+            x[4 * j + 0] *= s4.x;
+            x[4 * j + 1] *= s4.y;
+            x[4 * j + 2] *= s4.z;
+            x[4 * j + 3] *= s4.w;
         }
     }
     if (ep.relu) {
@@ -83,7 +95,7 @@ __device__ __forceinline__ void epilogue_tile(const Epilogue& ep, const CUtensor
     const int64_t row = int64_t(m0) + rloc;
     bool valid = row < M;
     int64_t mirror_a = -1, mirror_b = -1;
-    int64_t grp = 0;
+    int64_t grp = 0, sgrp = 0;
     int64_t out_row = row;
     if (ep.img_Wp > 0) {
         const int64_t img = int64_t(ep.img_Hp) * ep.img_Wp;
@@ -91,12 +103,14 @@ __device__ __forceinline__ void epilogue_tile(const Epilogue& ep, const CUtensor
         const int rem = int(row - grp * img);
         const int h = rem / ep.img_Wp - 1, w = rem % ep.img_Wp - 1;
         valid = valid && h >= 0 && h < ep.img_H && w >= 0 && w < ep.img_W;
-        if (ep.img_stride == 2) valid = valid && ((h | w) & 1) == 0;
-        out_row = (grp * ep.out_Hp + h / ep.img_stride + 1) * ep.out_Wp + w / ep.img_stride + 1;
+        const int sw = ep.img_stride_w ? ep.img_stride_w : ep.img_stride;
+        valid = valid && (h % ep.img_stride) == 0 && (w % sw) == 0;
+        out_row = (grp * ep.out_Hp + h / ep.img_stride + 1) * ep.out_Wp + w / sw + 1;
     } else if (ep.Tp > 0) {
         grp = row / ep.Tp;
         const int t = int(row - grp * ep.Tp) - ep.P;
         valid = valid && t >= 0 && t < ep.T;
+        if (ep.seg_scale && valid) sgrp = grp * ep.nseg + t / ep.seg_len;
         if (ep.halo && valid) {
             if (t >= 1 && t <= ep.P) mirror_a = row - 2 * t;
             const int u = ep.T - 1 - t;  // distance from the last frame
@@ -121,8 +135,8 @@ __device__ __forceinline__ void epilogue_tile(const Epilogue& ep, const CUtensor
             tmem_ld32(t_addr + c * 32, v);
             tmem_ld_wait();
             float x[32];
-            if (col < N) {
-                epilogue_math(ep, N, col, gsafe, v, x);
+            if (col < N && (valid || !ep.zero_invalid)) {
+                epilogue_math(ep, N, col, gsafe, sgrp, v, x);
             } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) x[j] = 0.f;
@@ -168,7 +182,7 @@ __device__ __forceinline__ void epilogue_tile(const Epilogue& ep, const CUtensor
         if (!valid || col >= N || ep.debug_nostore) continue;
         float x[32];
         if (col + 32 <= N) {
-            epilogue_math(ep, N, col, grp, v, x);
+            epilogue_math(ep, N, col, grp, sgrp, v, x);
         } else {  // ragged N (cosine scoring): no per-column vectors on this path
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);

@@ -44,6 +44,14 @@ class ERes2NetCfg(C.Structure):
                 ("precision", C.c_int)]
 
 
+PPV_MODEL_CAMPPLUS = 4
+
+
+class CamPPlusCfg(C.Structure):
+    _fields_ = [("input_size", C.c_int), ("embd_dim", C.c_int), ("growth_rate", C.c_int), ("bn_size", C.c_int),
+                ("init_channels", C.c_int), ("precision", C.c_int)]
+
+
 _P = C.c_void_p
 # name -> (restype, argtypes); this table is also what tests/test_abi.py checks against include/ppv_b200.h
 SIGNATURES = {
@@ -59,6 +67,7 @@ SIGNATURES = {
     "ppv_ecapa_default_cfg": (None, [C.POINTER(EcapaCfg)]),
     "ppv_resnetse_default_cfg": (None, [C.POINTER(ResNetSECfg)]),
     "ppv_eres2net_default_cfg": (None, [C.POINTER(ERes2NetCfg)]),
+    "ppv_campplus_default_cfg": (None, [C.POINTER(CamPPlusCfg)]),
     "ppv_model_create": (C.c_int, [C.c_int, _P, C.POINTER(_P)]),
     "ppv_model_destroy": (C.c_int, [_P]),
     "ppv_model_load_weight": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int]),
