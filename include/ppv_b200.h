@@ -68,6 +68,52 @@ int ppv_fbank_forward(ppv_fbank_t* h, const float* wav, const float* lens_ratio,
                       void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * STFT front ends.  Replace paddle.audio.features.{Spectrogram, MelSpectrogram, LogMelSpectrogram, MFCC} as
+ * constructed by ppvector/data_utils/featurizer.py:20-27, plus featurizer.py:43-59 (transpose, time-mean
+ * subtraction, tail mask).  Defaults of ppv_spectral_default_cfg are the library's own (sr 22050, n_fft 2048
+ * (Spectrogram: 512), hop 512, hann, centred with reflect padding, power 2 (Spectrogram: 1), 64 slaney mels from
+ * 50 Hz, amin 1e-10, ref 1, top_db None, 40 MFCCs with an orthonormal DCT-II).  top_db is not implemented.
+ * ------------------------------------------------------------------------------------------- */
+#define PPV_SPEC_SPECTROGRAM 1
+#define PPV_SPEC_MEL 2
+#define PPV_SPEC_LOGMEL 3
+#define PPV_SPEC_MFCC 4
+typedef struct {
+    int method;      /* PPV_SPEC_* */
+    int sample_rate; /* 22050 */
+    int n_fft;       /* power of two in [32, 4096] */
+    int hop_length;  /* 512 */
+    int win_length;  /* 0 => n_fft */
+    float power;     /* exponent of |X| */
+    int center;      /* 1: reflect-pad n_fft/2 on both sides */
+    int n_mels;      /* 64 */
+    float f_min;     /* 50 */
+    float f_max;     /* 0 => sample_rate / 2 */
+    int htk;         /* 0: slaney mel scale */
+    int norm_slaney; /* 1: area-normalised filters */
+    float ref_value; /* 1 */
+    float amin;      /* 1e-10 */
+    int n_mfcc;      /* 40 */
+} ppv_spectral_cfg;
+typedef struct ppv_spectral ppv_spectral_t;
+void ppv_spectral_default_cfg(ppv_spectral_cfg* cfg, int method);
+int ppv_spectral_create(const ppv_spectral_cfg* cfg, ppv_spectral_t** out);
+int ppv_spectral_destroy(ppv_spectral_t* h);
+/* centred: 1 + L / hop (needs L > n_fft / 2); else 1 + (L - n_fft) / hop. */
+int ppv_spectral_num_frames(const ppv_spectral_t* h, int L);
+int ppv_spectral_feature_dim(const ppv_spectral_t* h);
+/* wav [B,L] fp32 -> out [B,T,F] fp32, time-mean subtracted, optional tail mask as in ppv_fbank_forward. */
+int ppv_spectral_forward(ppv_spectral_t* h, const float* wav, const float* lens_ratio, int B, int L, float* out, void* stream);
+
+/* SpecAugment masking of a feature batch in place (ppvector/data_utils/reader.py:105-107, configs/augmentation.yml:36-48,
+ * max_time_warp 0).  The random draws stay on the host, made with the reference's RNG calls; params is int32
+ * [B][PPV_SPECAUG_NPARAM] on the device: {apply (0/1), T_b = frames of utterance b, n_freq_masks x (f0, width),
+ * n_time_masks x (t0, width)}.  fill_mode 0 writes zeros, 1 the utterance's mean over its T_b x F values before masking. */
+#define PPV_SPECAUG_NPARAM 16
+int ppv_spec_augment(float* feat, const int32_t* params, int B, int T, int F, int n_freq_masks, int n_time_masks, int fill_mode,
+                     void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Speaker-embedding model.  Replaces <Model>.forward, reached from
  * ppvector/predict.py:228-233, :265-266 and ppvector/trainer.py:391-410 (eval mode, lengths=None).
  * kind PPV_MODEL_ECAPA_TDNN: ppvector/models/ecapa_tdnn.py:245-276 with

@@ -42,6 +42,10 @@ using namespace ppv;
 struct ppv_fbank {
     Fbank* impl;
 };
+struct ppv_spectral {
+    Spectral* impl;
+};
+
 struct ppv_model {
     int kind;
     EcapaModel* ecapa;
@@ -261,6 +265,43 @@ int ppv_model_profile_read(ppv_model_t* h, double* gemm_ms, double* other_ms, in
     PPV_GUARD_BEGIN
     PPV_REQUIRE(h && h->ecapa, "ppv_model_profile_read: ECAPA-TDNN model required");
     return ecapa_profile_read(h->ecapa, gemm_ms, other_ms, gemm_launches, other_launches);
+    PPV_GUARD_END
+}
+
+// ---------------------------------------------------------------- STFT front ends, SpecAugment
+void ppv_spectral_default_cfg(ppv_spectral_cfg* c, int method) {
+    if (c) spectral_default_cfg(c, method);
+}
+int ppv_spectral_create(const ppv_spectral_cfg* cfg, ppv_spectral_t** out) {
+    PPV_GUARD_BEGIN
+    PPV_REQUIRE(cfg && out, "ppv_spectral_create: null argument");
+    int rc = check_device();
+    if (rc) return rc;
+    Spectral* impl = nullptr;
+    rc = spectral_create(cfg, &impl);
+    if (rc) return rc;
+    *out = new ppv_spectral{impl};
+    return PPV_OK;
+    PPV_GUARD_END
+}
+int ppv_spectral_destroy(ppv_spectral_t* h) {
+    if (!h) return PPV_OK;
+    spectral_destroy(h->impl);
+    delete h;
+    return PPV_OK;
+}
+int ppv_spectral_num_frames(const ppv_spectral_t* h, int L) { return h ? spectral_num_frames(h->impl, L) : 0; }
+int ppv_spectral_feature_dim(const ppv_spectral_t* h) { return h ? spectral_feature_dim(h->impl) : 0; }
+int ppv_spectral_forward(ppv_spectral_t* h, const float* wav, const float* lens_ratio, int B, int L, float* out, void* stream) {
+    PPV_GUARD_BEGIN
+    PPV_REQUIRE(h && wav && out, "ppv_spectral_forward: null argument");
+    PPV_REQUIRE(B > 0 && L > 0, "ppv_spectral_forward: empty input");
+    return spectral_run(h->impl, wav, lens_ratio, B, L, out, static_cast<cudaStream_t>(stream));
+    PPV_GUARD_END
+}
+int ppv_spec_augment(float* feat, const int32_t* params, int B, int T, int F, int n_freq_masks, int n_time_masks, int fill_mode, void* stream) {
+    PPV_GUARD_BEGIN
+    return spec_augment_run(feat, params, B, T, F, n_freq_masks, n_time_masks, fill_mode, static_cast<cudaStream_t>(stream));
     PPV_GUARD_END
 }
 

@@ -203,6 +203,16 @@ int fbank_n_mels(const Fbank* h);
 int fbank_run(Fbank* h, const float* wav, const float* lens_ratio, int B, int L, float* raw, float* out_f32,
               const Planes& out_pl, int P, int Tp, cudaStream_t st);
 
+// ---- spectral.cu ------------------------------------------------------------------------------------
+struct Spectral;
+void spectral_default_cfg(ppv_spectral_cfg* c, int method);
+int spectral_create(const ppv_spectral_cfg* cfg, Spectral** out);
+void spectral_destroy(Spectral* h);
+int spectral_num_frames(const Spectral* h, int L);
+int spectral_feature_dim(const Spectral* h);
+int spectral_run(Spectral* h, const float* wav, const float* lens_ratio, int B, int L, float* out, cudaStream_t st);
+int spec_augment_run(float* feat, const int32_t* params, int B, int T, int F, int n_freq_masks, int n_time_masks, int fill_mode, cudaStream_t st);
+
 // ---- ecapa.cu ---------------------------------------------------------------------------------------
 struct EcapaModel;
 int ecapa_create(const ppv_ecapa_cfg* cfg, EcapaModel** out);

@@ -45,6 +45,14 @@ class ERes2NetCfg(C.Structure):
 
 
 PPV_MODEL_CAMPPLUS = 4
+PPV_SPEC_SPECTROGRAM, PPV_SPEC_MEL, PPV_SPEC_LOGMEL, PPV_SPEC_MFCC = 1, 2, 3, 4
+PPV_SPECAUG_NPARAM = 16
+
+
+class SpectralCfg(C.Structure):
+    _fields_ = [("method", C.c_int), ("sample_rate", C.c_int), ("n_fft", C.c_int), ("hop_length", C.c_int), ("win_length", C.c_int),
+                ("power", C.c_float), ("center", C.c_int), ("n_mels", C.c_int), ("f_min", C.c_float), ("f_max", C.c_float),
+                ("htk", C.c_int), ("norm_slaney", C.c_int), ("ref_value", C.c_float), ("amin", C.c_float), ("n_mfcc", C.c_int)]
 
 
 class CamPPlusCfg(C.Structure):
@@ -64,6 +72,13 @@ SIGNATURES = {
     "ppv_fbank_num_frames": (C.c_int, [_P, C.c_int]),
     "ppv_fbank_feature_dim": (C.c_int, [_P]),
     "ppv_fbank_forward": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P]),
+    "ppv_spectral_default_cfg": (None, [C.POINTER(SpectralCfg), C.c_int]),
+    "ppv_spectral_create": (C.c_int, [C.POINTER(SpectralCfg), C.POINTER(_P)]),
+    "ppv_spectral_destroy": (C.c_int, [_P]),
+    "ppv_spectral_num_frames": (C.c_int, [_P, C.c_int]),
+    "ppv_spectral_feature_dim": (C.c_int, [_P]),
+    "ppv_spectral_forward": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P]),
+    "ppv_spec_augment": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "ppv_ecapa_default_cfg": (None, [C.POINTER(EcapaCfg)]),
     "ppv_resnetse_default_cfg": (None, [C.POINTER(ResNetSECfg)]),
     "ppv_eres2net_default_cfg": (None, [C.POINTER(ERes2NetCfg)]),

@@ -3,7 +3,8 @@
 Same constructor (``feature_method``, ``method_args``), same ``forward(waveforms, input_lens_ratio=None)``
 contract ([B,L] or [L] float32 in [-1,1] -> [B,T,F] float32, per-utterance time mean subtracted, optional
 tail mask applied after the mean subtraction), same ``feature_dim`` property.  The arithmetic runs in one
-fused CUDA kernel family (``csrc/fbank.cu``) behind ``ppv_fbank_forward``.
+fused CUDA kernel family behind the C ABI: ``csrc/fbank.cu`` (``ppv_fbank_forward``) for ``Fbank``, ``csrc/spectral.cu``
+(``ppv_spectral_forward``) for the ``paddle.audio.features`` methods (Spectrogram, MelSpectrogram, LogMelSpectrogram, MFCC).
 """
 import ctypes as C
 
@@ -22,11 +23,43 @@ class AudioFeaturizer(torch.nn.Module):
         self._handle = None
         if feature_method == 'Fbank':
             self._cfg = self._fbank_cfg(self._method_args)
-        elif feature_method in ('LogMelSpectrogram', 'MelSpectrogram', 'Spectrogram', 'MFCC'):
-            # the paddle.audio.features front ends are "next"; no silent fallback.
-            raise _lib.PPVError(f'预处理方法 {feature_method} 尚未在 B200 路径实现 (only Fbank is implemented)')
+        elif feature_method in self._SPECTRAL:
+            self._cfg = self._spectral_cfg(feature_method, self._method_args)
         else:
             raise Exception(f'预处理方法 {self._feature_method} 不存在!')  # featurizer.py:31
+
+    _SPECTRAL = {'Spectrogram': _lib.PPV_SPEC_SPECTROGRAM, 'MelSpectrogram': _lib.PPV_SPEC_MEL,
+                 'LogMelSpectrogram': _lib.PPV_SPEC_LOGMEL, 'MFCC': _lib.PPV_SPEC_MFCC}
+
+    @classmethod
+    def _spectral_cfg(cls, method, args):
+        """paddle.audio.features.<method>(**method_args) keyword names -> ppv_spectral_cfg"""
+        lib = _lib.load()
+        cfg = _lib.SpectralCfg()
+        lib.ppv_spectral_default_cfg(C.byref(cfg), cls._SPECTRAL[method])
+        direct = {'sr': 'sample_rate', 'n_fft': 'n_fft', 'hop_length': 'hop_length', 'power': 'power', 'n_mels': 'n_mels',
+                  'f_min': 'f_min', 'ref_value': 'ref_value', 'amin': 'amin', 'n_mfcc': 'n_mfcc'}
+        for k, v in args.items():
+            if k in direct:
+                setattr(cfg, direct[k], type(getattr(cfg, direct[k]))(v))
+            elif k == 'win_length':
+                cfg.win_length = 0 if v is None else int(v)
+            elif k == 'f_max':
+                cfg.f_max = 0.0 if v is None else float(v)
+            elif k == 'htk':
+                cfg.htk = int(bool(v))
+            elif k == 'norm':
+                if v not in ('slaney', None):
+                    raise _lib.PPVError(f'{method}: norm={v!r} is not supported by the B200 kernel (slaney or None)')
+                cfg.norm_slaney = int(v == 'slaney')
+            elif k == 'center':
+                cfg.center = int(bool(v))
+            elif k == 'window' and v == 'hann' or k == 'pad_mode' and v == 'reflect' or k == 'dtype' and v == 'float32' \
+                    or k == 'top_db' and v is None:
+                pass
+            else:
+                raise _lib.PPVError(f'{method} argument {k}={v!r} is not supported by the B200 kernel')
+        return cfg
 
     @staticmethod
     def _fbank_cfg(args):
@@ -48,20 +81,26 @@ class AudioFeaturizer(torch.nn.Module):
         if self._handle is None:
             lib = _lib.load()
             h = C.c_void_p()
-            _lib.check(lib.ppv_fbank_create(C.byref(self._cfg), C.byref(h)), 'ppv_fbank_create')
+            if self._feature_method == 'Fbank':
+                _lib.check(lib.ppv_fbank_create(C.byref(self._cfg), C.byref(h)), 'ppv_fbank_create')
+            else:
+                _lib.check(lib.ppv_spectral_create(C.byref(self._cfg), C.byref(h)), 'ppv_spectral_create')
             self._handle = h
         return self._handle
 
     def __del__(self):
         try:
             if self._handle is not None:
-                _lib.load().ppv_fbank_destroy(self._handle)
+                lib = _lib.load()
+                (lib.ppv_fbank_destroy if self._feature_method == 'Fbank' else lib.ppv_spectral_destroy)(self._handle)
                 self._handle = None
         except Exception:
             pass
 
     def num_frames(self, num_samples: int) -> int:
-        return _lib.load().ppv_fbank_num_frames(self._get_handle(), int(num_samples))
+        lib = _lib.load()
+        fn = lib.ppv_fbank_num_frames if self._feature_method == 'Fbank' else lib.ppv_spectral_num_frames
+        return fn(self._get_handle(), int(num_samples))
 
     def forward(self, waveforms, input_lens_ratio=None):
         """reference: featurizer.py:33-60"""
@@ -74,17 +113,23 @@ class AudioFeaturizer(torch.nn.Module):
         B, L = wav.shape
         lib = _lib.load()
         h = self._get_handle()
-        T = lib.ppv_fbank_num_frames(h, L)
+        fbank = self._feature_method == 'Fbank'
+        T = (lib.ppv_fbank_num_frames if fbank else lib.ppv_spectral_num_frames)(h, L)
         if T <= 0:
             raise _lib.PPVError(f'waveform of {L} samples is shorter than one frame')
         ratio = None
         if input_lens_ratio is not None:
             ratio = torch.as_tensor(input_lens_ratio, dtype=torch.float32, device=wav.device).contiguous()
             assert ratio.numel() == B
-        out = torch.empty((B, T, self._cfg.n_mels), dtype=torch.float32, device=wav.device)
+        F = self._cfg.n_mels if fbank else lib.ppv_spectral_feature_dim(h)
+        out = torch.empty((B, T, F), dtype=torch.float32, device=wav.device)
         with torch.cuda.device(wav.device):
-            _lib.check(lib.ppv_fbank_forward(h, _lib.ptr(wav), _lib.ptr(ratio), B, L, _lib.ptr(out),
-                                             _lib.current_stream()), 'ppv_fbank_forward')
+            if fbank:
+                _lib.check(lib.ppv_fbank_forward(h, _lib.ptr(wav), _lib.ptr(ratio), B, L, _lib.ptr(out),
+                                                 _lib.current_stream()), 'ppv_fbank_forward')
+            else:
+                _lib.check(lib.ppv_spectral_forward(h, _lib.ptr(wav), _lib.ptr(ratio), B, L, _lib.ptr(out),
+                                                    _lib.current_stream()), 'ppv_spectral_forward')
         return out
 
     @property

@@ -2,9 +2,9 @@
 
 List file lines are ``path\\tlabel``; items are ``(feature [T,F] float32 CUDA tensor, speaker id)``.  Audio goes
 wav -> float32 -> (resample) -> dB normalise -> crop (eval: from 0; train: random start; extract_feature: no crop) ->
-``AudioFeaturizer`` on the GPU.  ``.npy`` entries are pre-extracted features (reader.py:78-83).  Waveform augmentation
-(speed / volume / noise / reverb, yeaudio) and SpecAugment are not implemented on the B200 path: passing ``aug_conf``
-raises instead of silently skipping them."""
+``AudioFeaturizer`` on the GPU -> SpecAugment (train mode, reader.py:105-107, ``ppv_spec_augment``).  ``.npy`` entries are
+pre-extracted features (reader.py:78-83).  Waveform augmentation (speed / volume / noise / reverb, yeaudio) is not implemented
+on the B200 path: an ``aug_conf`` that enables any of them raises instead of silently skipping it."""
 import random
 
 import numpy as np
@@ -13,6 +13,7 @@ from tqdm import tqdm
 
 from ppvector.data_utils.audio import AudioSegment
 from ppvector.data_utils.featurizer import AudioFeaturizer
+from ppvector.data_utils.spec_aug import SpecAugmentor
 
 
 class PPVectorDataset(torch.utils.data.Dataset):
@@ -21,8 +22,17 @@ class PPVectorDataset(torch.utils.data.Dataset):
                  device='cuda'):
         super().__init__()
         assert mode in ['train', 'eval', 'extract_feature']
+        self.spec_augment = None
         if mode == 'train' and aug_conf is not None:
-            raise NotImplementedError('data augmentation is not implemented on the B200 path (SURVEY.md §2 row 13)')
+            conf = dict(aug_conf) if isinstance(aug_conf, dict) else dict(vars(aug_conf))
+            for name in ('speed', 'volume', 'noise', 'reverb'):
+                sub = conf.get(name)
+                prob = (sub.get('prob', 0) if isinstance(sub, dict) else getattr(sub, 'prob', 0)) if sub is not None else 0
+                if prob and prob > 0:
+                    raise NotImplementedError(f'{name} augmentation is not implemented on the B200 path (SURVEY.md §2 row 13); set its prob to 0')
+            sa = conf.get('spec_aug')
+            if sa is not None:  # reader.py:150-151
+                self.spec_augment = SpecAugmentor(**(dict(sa) if isinstance(sa, dict) else dict(vars(sa))))
         self.data_list_path = data_list_path
         self.max_duration, self.min_duration, self.mode = max_duration, min_duration, mode
         self._target_sample_rate = sample_rate
@@ -65,8 +75,11 @@ class PPVectorDataset(torch.utils.data.Dataset):
             if feature.shape[0] > self.max_feature_len:
                 s = random.randint(0, feature.shape[0] - self.max_feature_len) if self.mode == 'train' else 0
                 feature = feature[s:s + self.max_feature_len, :]
-            return torch.from_numpy(feature.astype(np.float32)).to(self.device), spk_id
-        feature = self.audio_featurizer(torch.from_numpy(x).to(self.device)).squeeze(0)
+            feature = torch.from_numpy(feature.astype(np.float32)).to(self.device)
+        else:
+            feature = self.audio_featurizer(torch.from_numpy(x).to(self.device)).squeeze(0)
+        if self.mode == 'train' and self.spec_augment is not None:  # reader.py:105-107
+            feature = self.spec_augment(feature)
         return feature, spk_id
 
     def __len__(self):
