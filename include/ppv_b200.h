@@ -204,6 +204,35 @@ int ppv_model_profile_read(ppv_model_t* h, double* gemm_ms, double* other_ms, in
                            int64_t* other_launches);
 
 /* ---------------------------------------------------------------------------------------------
+ * Training step (ECAPA-TDNN).  Replaces the body of PPVectorTrainer.__train_epoch, ppvector/trainer.py:206-229:
+ *   outputs = model(features); los = loss(outputs, label); los.backward(); optimizer.step(); optimizer.clear_grad()
+ * with the model in TRAIN mode (BatchNorm batch statistics, running statistics updated with momentum 0.9), the classifier
+ * ppvector/models/fc.py:41-53 and AAMLoss ppvector/loss/aamloss.py:28-53, Adam ppvector/optimizer/__init__.py:12-18
+ * (coupled L2 weight decay).  Parameters / gradients / BatchNorm running statistics are three caller-owned flat fp32 device
+ * buffers; ppv_trainer_lookup gives each state_dict tensor's offset ("blocks.1.tdnn1.conv.conv.weight", ...,
+ * "classifier.weight" [embd_dim, num_classes]; "*._mean" / "*._variance" live in the statistics buffer).  Data-parallel
+ * training is one all-reduce(sum) over the gradient buffer followed by ppv_adam_step(grad_scale = 1 / nranks)
+ * (the reference's fleet.distributed_model, trainer.py:318-320).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ppv_trainer ppv_trainer_t;
+int ppv_trainer_create(const ppv_ecapa_cfg* cfg, int num_classes, ppv_trainer_t** out);
+int ppv_trainer_destroy(ppv_trainer_t* h);
+int64_t ppv_trainer_param_count(const ppv_trainer_t* h); /* floats in the parameter / gradient buffers (tensors are 32-byte aligned) */
+int64_t ppv_trainer_stat_count(const ppv_trainer_t* h);  /* floats in the running-statistics buffer */
+int ppv_trainer_lookup(const ppv_trainer_t* h, const char* name, int64_t* offset, int64_t* numel, int* is_stat);
+int ppv_trainer_bind(ppv_trainer_t* h, float* params, float* grads, float* stats);
+size_t ppv_trainer_workspace_bytes(ppv_trainer_t* h, int B, int T);
+/* feat [B,T,F] fp32, labels [B] int64 (device).  Overwrites the whole gradient buffer with d(loss)/d(param), updates the
+ * running statistics, writes the scalar loss and (optionally) the cosine logits [B, num_classes] (device pointers). */
+int ppv_trainer_forward_backward(ppv_trainer_t* h, const float* feat, const int64_t* labels, int B, int T, float margin, float scale,
+                                 int easy_margin, float label_smoothing, float* loss, float* logits, void* ws, size_t ws_bytes, void* stream);
+/* forward activations of the last step: "blocks.0".."blocks.3", "mfa" -> [B,T,C]; "asp" -> [B, 2*3C]; "emb" -> [B, embd_dim] */
+int ppv_trainer_read_tap(ppv_trainer_t* h, const char* name, float* out, size_t out_elems, void* stream);
+/* p -= lr * mhat / (sqrt(vhat) + eps) with g = grads * grad_scale + weight_decay * p; step counts from 1. */
+int ppv_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, int64_t step, float grad_scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Cosine scoring.  Replaces ppvector/predict.py:279-283 (contrast), :173-187 (retrieval:
  * sklearn cosine_similarity) and ppvector/trainer.py:416-423 (eval trial x enrol matrix).
  * ------------------------------------------------------------------------------------------- */

@@ -46,13 +46,18 @@ def batchnorm_eval(x, W: Dict[str, torch.Tensor], prefix: str):
     return (x - m.view(shape)) / torch.sqrt(v.view(shape) + BN_EPS) * g.view(shape) + b.view(shape)
 
 
-def tdnn_block(x, W, prefix, dilation=1):
-    """utils.py:147  return self.norm(self.activation(self.conv(x)))"""
+def tdnn_block(x, W, prefix, dilation=1, bn=batchnorm_eval, taps=None):
+    """utils.py:147  return self.norm(self.activation(self.conv(x)));  ``bn`` = batchnorm_eval or a train-mode BatchNorm
+    (oracle/train.py)"""
     y = conv1d_same_reflect(x, W[prefix + ".conv.conv.weight"], W[prefix + ".conv.conv.bias"], dilation)
-    return batchnorm_eval(F.relu(y), W, prefix + ".norm.norm")
+    out = bn(F.relu(y), W, prefix + ".norm.norm")
+    if taps is not None:  # layer-level taps (gradient localisation in tests): conv output and block output
+        taps[prefix + ".z"] = y
+        taps[prefix] = out
+    return out
 
 
-def res2net_block(x, W, prefix, scale=8, dilation=1):
+def res2net_block(x, W, prefix, scale=8, dilation=1, bn=batchnorm_eval, taps=None):
     """ecapa_tdnn.py:36-47"""
     ys = []
     y_i = None
@@ -60,9 +65,9 @@ def res2net_block(x, W, prefix, scale=8, dilation=1):
         if i == 0:
             y_i = x_i
         elif i == 1:
-            y_i = tdnn_block(x_i, W, f"{prefix}.blocks.{i - 1}", dilation)
+            y_i = tdnn_block(x_i, W, f"{prefix}.blocks.{i - 1}", dilation, bn, taps)
         else:
-            y_i = tdnn_block(x_i + y_i, W, f"{prefix}.blocks.{i - 1}", dilation)
+            y_i = tdnn_block(x_i + y_i, W, f"{prefix}.blocks.{i - 1}", dilation, bn, taps)
         ys.append(y_i)
     return torch.cat(ys, dim=1)
 
@@ -86,19 +91,21 @@ def se_block(x, W, prefix, lengths=None):
     return s * x
 
 
-def se_res2net_block(x, W, prefix, scale=8, dilation=1, lengths=None):
+def se_res2net_block(x, W, prefix, scale=8, dilation=1, lengths=None, bn=batchnorm_eval, taps=None):
     """ecapa_tdnn.py:132-142 (in_channels == out_channels for the shipped config -> no shortcut conv)"""
     residual = x
     if prefix + ".shortcut.conv.weight" in W:
         residual = F.conv1d(x, W[prefix + ".shortcut.conv.weight"], W[prefix + ".shortcut.conv.bias"])
-    x = tdnn_block(x, W, prefix + ".tdnn1")
-    x = res2net_block(x, W, prefix + ".res2net_block", scale, dilation)
-    x = tdnn_block(x, W, prefix + ".tdnn2")
+    x = tdnn_block(x, W, prefix + ".tdnn1", bn=bn, taps=taps)
+    x = res2net_block(x, W, prefix + ".res2net_block", scale, dilation, bn, taps)
+    if taps is not None:
+        taps[prefix + ".res2net_block"] = x
+    x = tdnn_block(x, W, prefix + ".tdnn2", bn=bn, taps=taps)
     x = se_block(x, W, prefix + ".se_block", lengths)
     return x + residual
 
 
-def attentive_stats_pool(x, W, prefix="asp", lengths=None, global_context=True):
+def attentive_stats_pool(x, W, prefix="asp", lengths=None, global_context=True, bn=batchnorm_eval):
     """pooling.py:86-125"""
     N, C, L = x.shape
 
@@ -116,7 +123,7 @@ def attentive_stats_pool(x, W, prefix="asp", lengths=None, global_context=True):
         attn = torch.cat([x, mean.unsqueeze(2).expand(-1, -1, L), std.unsqueeze(2).expand(-1, -1, L)], dim=1)
     else:
         attn = x
-    attn = torch.tanh(tdnn_block(attn, W, prefix + ".tdnn"))
+    attn = torch.tanh(tdnn_block(attn, W, prefix + ".tdnn", bn=bn))
     attn = F.conv1d(attn, W[prefix + ".conv.conv.weight"], W[prefix + ".conv.conv.bias"])
     attn = attn.masked_fill(mask.expand(-1, C, -1) == 0, float("-inf"))
     attn = F.softmax(attn, dim=2)
@@ -125,7 +132,7 @@ def attentive_stats_pool(x, W, prefix="asp", lengths=None, global_context=True):
 
 
 def ecapa_forward(feats, W: Dict[str, torch.Tensor], lengths: Optional[torch.Tensor] = None,
-                  dilations=(1, 2, 3, 4, 1), res2net_scale=8, taps: Optional[dict] = None):
+                  dilations=(1, 2, 3, 4, 1), res2net_scale=8, taps: Optional[dict] = None, bn=batchnorm_eval, layer_taps=False):
     """ecapa_tdnn.py:245-276.  feats [B,T,F] -> embedding [B,embd_dim].
 
     ``taps`` (optional dict) is filled with intermediate activations for per-layer
@@ -133,24 +140,24 @@ def ecapa_forward(feats, W: Dict[str, torch.Tensor], lengths: Optional[torch.Ten
     """
     x = feats.transpose(1, 2)
     xl = []
-    x = tdnn_block(x, W, "blocks.0", dilations[0])
+    x = tdnn_block(x, W, "blocks.0", dilations[0], bn)
     xl.append(x)
     if taps is not None:
         taps["blocks.0"] = x
     nblk = len(dilations) - 2
     for i in range(1, nblk + 1):
-        x = se_res2net_block(x, W, f"blocks.{i}", res2net_scale, dilations[i], lengths)
+        x = se_res2net_block(x, W, f"blocks.{i}", res2net_scale, dilations[i], lengths, bn, taps if layer_taps else None)
         xl.append(x)
         if taps is not None:
             taps[f"blocks.{i}"] = x
     x = torch.cat(xl[1:], dim=1)
-    x = tdnn_block(x, W, "mfa", dilations[-1])
+    x = tdnn_block(x, W, "mfa", dilations[-1], bn)
     if taps is not None:
         taps["mfa"] = x
-    x = attentive_stats_pool(x, W, "asp", lengths)
+    x = attentive_stats_pool(x, W, "asp", lengths, bn=bn)
     if taps is not None:
         taps["asp"] = x
-    x = batchnorm_eval(x, W, "asp_bn.norm")
+    x = bn(x, W, "asp_bn.norm")
     x = F.conv1d(x.unsqueeze(2), W["fc.conv.weight"], W["fc.conv.bias"]).squeeze(-1)
     return x
 

@@ -1,0 +1,115 @@
+"""GPU: the ECAPA-TDNN training step vs torch autograd over the fp64 oracle: train-mode forward taps,
+loss, EVERY parameter gradient, BatchNorm running statistics, and a short Adam loss curve.
+
+Tolerances.  Activations and activation gradients are stored as split-bf16 planes (16 mantissa bits, 2^-17 relative), the
+contraction is the 3-pass bf16 one: the forward agrees with fp64 to ~3e-5, the gradients of the head to ~5e-5.  Each train-mode
+BatchNorm backward projects out the mean and the x-hat component of its incoming gradient, which amplifies the relative error of
+what is left, so the error grows towards the input: ~2e-4 below the pooling layer, ~5e-3 at the first conv (measured,
+tools/train_grad_check.py).  The reference trains with fp16 autocast (trainer.py:209) at a far looser precision.  Asserted here:
+every parameter gradient within 5e-2 relative (L2, per tensor; the worst are 64-element bias gradients, sums that cancel) with
+cosine > 0.999 to the fp64 gradient, and the head within 5e-4."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ecapa as oe
+from oracle import train as ot
+from ppvector.train_engine import TrainEngine
+
+pytestmark = pytest.mark.gpu
+
+S = 37
+
+
+def make_problem(B, T, seed):
+    g = torch.Generator().manual_seed(seed)
+    f = torch.randn(B, T, 80, generator=g, dtype=torch.float64)
+    f = f - f.mean(1, keepdim=True)
+    y = torch.randint(0, S, (B,), generator=g)
+    Wc = (torch.rand(192, S, generator=g, dtype=torch.float64) * 2 - 1) * (6.0 / (192 + S)) ** 0.5
+    return f, y, Wc
+
+
+@pytest.fixture(scope="module")
+def W64():
+    return oe.make_ecapa_weights(seed=1000, dtype=torch.float64)
+
+
+def new_engine(cuda, W64, Wc):
+    eng = TrainEngine(input_size=80, num_speakers=S, device=cuda)
+    eng.load_state_dict(W64, Wc)
+    return eng
+
+
+@pytest.mark.parametrize("B,T,margin,ls", [(4, 40, 0.2, 0.0), (3, 61, 0.0, 0.1)])
+def test_forward_taps_loss_and_all_gradients(cuda, W64, B, T, margin, ls):
+    f, y, Wc = make_problem(B, T, 100 + T)
+    taps = {}
+    loss, grads, stats, logits = ot.train_step_grads(f, y, W64, Wc, margin=margin, label_smoothing=ls, taps=taps)
+    eng = new_engine(cuda, W64, Wc)
+    got_loss, got_logits = eng.forward_backward(f.float().to(cuda), y.to(cuda), margin=margin, label_smoothing=ls, return_logits=True)
+    torch.cuda.synchronize()
+    for name, C in [("blocks.0", 512), ("blocks.1", 512), ("blocks.2", 512), ("blocks.3", 512), ("mfa", 1536)]:
+        got = eng.read_tap(name, (B, T, C)).double().cpu()
+        want = taps[name].transpose(1, 2)
+        rel = (got - want).norm() / want.norm()
+        assert rel < 5e-5, (name, rel.item())
+    for name, want in [("asp", taps["asp"]), ("emb", taps["emb"])]:
+        got = eng.read_tap(name, tuple(want.shape)).double().cpu()
+        assert (got - want).norm() / want.norm() < 1e-4, name
+    assert (got_logits.double().cpu() - logits).abs().max() < 1e-4
+    assert abs(got_loss.item() - loss.item()) < 1e-3 * max(1.0, abs(loss.item()))
+    bad = []
+    for name, gw in grads.items():
+        gg = eng.view(name, tuple(gw.shape), "grad").double().cpu()
+        if name == "asp.conv.conv.bias":  # softmax over time is shift invariant: this gradient is exactly zero in exact arithmetic
+            assert gw.abs().max() < 1e-12 and gg.abs().max() < 1e-4
+            continue
+        rel = ((gg - gw).norm() / (gw.norm() + 1e-12)).item()
+        cos = ((gg * gw).sum() / (gg.norm() * gw.norm() + 1e-30)).item()
+        head = name.startswith(("classifier", "fc.", "asp_bn."))
+        if not (rel < (5e-4 if head else 5e-2) and cos > 0.999):
+            bad.append((name, rel, cos, gw.norm().item()))
+    assert not bad, bad[:12]
+    for name, sw in stats.items():
+        gs = eng.view(name, tuple(sw.shape)).double().cpu()
+        assert (gs - sw).abs().max() < 1e-4 * max(1.0, sw.abs().max().item()), name
+
+
+def test_adam_loss_curve_matches_oracle(cuda, W64):
+    B, T, steps = 4, 33, 6
+    fs, ys = [], []
+    Wc = None
+    for i in range(steps):
+        f, y, w = make_problem(B, T, 500 + i)
+        fs.append(f)
+        ys.append(y)
+        Wc = w if Wc is None else Wc
+    margins = [ot.margin_at(i, 1, 5, 0.0, 0.3) for i in range(steps)]
+    want, W_end, Wc_end = ot.train_loop(fs, ys, W64, Wc, lr=1e-4, weight_decay=1e-6, margins=margins)
+    eng = new_engine(cuda, W64, Wc)
+    got = []
+    for i in range(steps):
+        loss = eng.forward_backward(fs[i].float().to(cuda), ys[i].to(cuda), margin=margins[i])
+        eng.adam_step(lr=1e-4, weight_decay=1e-6, grad_scale=eng.all_reduce_grads())
+        got.append(loss.item())
+    # Adam's early updates are ~lr * sign(g): where |g| is at the rounding level the sign is noise, so trajectories separate slowly
+    # (fp32 vs fp64 autograd of the oracle itself differ by 1e-3 after six steps at this learning rate)
+    assert np.allclose(got[:2], want[:2], rtol=2e-3), (got, want)
+    assert np.allclose(got, want, rtol=2e-2), (got, want)
+    # Adam's first steps move every weight by ~lr regardless of the gradient scale: compare the update direction loosely
+    for name in ["blocks.0.conv.conv.weight", "mfa.conv.conv.weight", "fc.conv.weight", "asp.tdnn.conv.conv.weight"]:
+        a = eng.view(name, tuple(W_end[name].shape)).double().cpu() - W64[name]
+        b = W_end[name] - W64[name]
+        cos = (a * b).sum() / (a.norm() * b.norm())
+        assert cos > 0.9, (name, cos.item())
+
+
+def test_step_is_bitwise_reproducible(cuda, W64):
+    f, y, Wc = make_problem(4, 40, 7)
+    eng = new_engine(cuda, W64, Wc)
+    eng.forward_backward(f.float().to(cuda), y.to(cuda))
+    g1 = eng.grads.clone()
+    eng.load_state_dict(W64, Wc)  # running statistics back to the start
+    eng.forward_backward(f.float().to(cuda), y.to(cuda))
+    assert torch.equal(g1, eng.grads)

@@ -46,6 +46,10 @@ struct ppv_spectral {
     Spectral* impl;
 };
 
+struct ppv_trainer {
+    Trainer* impl;
+};
+
 struct ppv_model {
     int kind;
     EcapaModel* ecapa;
@@ -302,6 +306,67 @@ int ppv_spectral_forward(ppv_spectral_t* h, const float* wav, const float* lens_
 int ppv_spec_augment(float* feat, const int32_t* params, int B, int T, int F, int n_freq_masks, int n_time_masks, int fill_mode, void* stream) {
     PPV_GUARD_BEGIN
     return spec_augment_run(feat, params, B, T, F, n_freq_masks, n_time_masks, fill_mode, static_cast<cudaStream_t>(stream));
+    PPV_GUARD_END
+}
+
+// ---------------------------------------------------------------- training step
+int ppv_trainer_create(const ppv_ecapa_cfg* cfg, int num_classes, ppv_trainer_t** out) {
+    PPV_GUARD_BEGIN
+    PPV_REQUIRE(cfg && out, "ppv_trainer_create: null argument");
+    int rc = check_device();
+    if (rc) return rc;
+    Trainer* impl = nullptr;
+    rc = trainer_create(cfg, num_classes, &impl);
+    if (rc) return rc;
+    *out = new ppv_trainer{impl};
+    return PPV_OK;
+    PPV_GUARD_END
+}
+int ppv_trainer_destroy(ppv_trainer_t* h) {
+    if (!h) return PPV_OK;
+    trainer_destroy(h->impl);
+    delete h;
+    return PPV_OK;
+}
+int64_t ppv_trainer_param_count(const ppv_trainer_t* h) { return h ? trainer_param_count(h->impl) : 0; }
+int64_t ppv_trainer_stat_count(const ppv_trainer_t* h) { return h ? trainer_stat_count(h->impl) : 0; }
+int ppv_trainer_lookup(const ppv_trainer_t* h, const char* name, int64_t* offset, int64_t* numel, int* is_stat) {
+    PPV_GUARD_BEGIN
+    PPV_REQUIRE(h, "ppv_trainer_lookup: null handle");
+    return trainer_lookup(h->impl, name, offset, numel, is_stat);
+    PPV_GUARD_END
+}
+int ppv_trainer_bind(ppv_trainer_t* h, float* params, float* grads, float* stats) {
+    PPV_GUARD_BEGIN
+    PPV_REQUIRE(h, "ppv_trainer_bind: null handle");
+    return trainer_bind(h->impl, params, grads, stats);
+    PPV_GUARD_END
+}
+size_t ppv_trainer_workspace_bytes(ppv_trainer_t* h, int B, int T) {
+    try {
+        return h ? trainer_workspace_bytes(h->impl, B, T) : 0;
+    } catch (...) {
+        return 0;
+    }
+}
+int ppv_trainer_forward_backward(ppv_trainer_t* h, const float* feat, const int64_t* labels, int B, int T, float margin, float scale,
+                                 int easy_margin, float label_smoothing, float* loss, float* logits, void* ws, size_t ws_bytes, void* stream) {
+    PPV_GUARD_BEGIN
+    PPV_REQUIRE(h, "ppv_trainer_forward_backward: null handle");
+    return trainer_forward_backward(h->impl, feat, labels, B, T, margin, scale, easy_margin, label_smoothing, loss, logits, ws, ws_bytes,
+                                    static_cast<cudaStream_t>(stream));
+    PPV_GUARD_END
+}
+int ppv_trainer_read_tap(ppv_trainer_t* h, const char* name, float* out, size_t out_elems, void* stream) {
+    PPV_GUARD_BEGIN
+    PPV_REQUIRE(h, "ppv_trainer_read_tap: null handle");
+    return trainer_read_tap(h->impl, name, out, out_elems, static_cast<cudaStream_t>(stream));
+    PPV_GUARD_END
+}
+int ppv_adam_step(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, int64_t step, float grad_scale, void* stream) {
+    PPV_GUARD_BEGIN
+    return adam_step(params, grads, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, static_cast<cudaStream_t>(stream));
     PPV_GUARD_END
 }
 

@@ -128,6 +128,9 @@ struct GemmParams {
     int num_ksteps;
     int bk;  // K elements per k-step (64 or 32)
     int l2_prefetch;  // producer prefetches the next tile's activation rows into L2
+    int lin_splits;   // > 0: weight-gradient mode (see gemm_build_wgrad): K runs over operand columns, split in lin_splits parts
+    int lin_b_row0, lin_b_col0;
+    int64_t lin_split_rows;
     int M, N;
     int m_tiles, n_tiles;
     Epilogue epi;
@@ -145,6 +148,8 @@ struct GemmSource {
 //   PPV_PREC_BF16  : A_hi*B_hi only
 int gemm_build(GemmParams* gp, const GemmSource* srcs, int nsrc, const Planes& W, int M, int N, const Epilogue& epi,
                int BN, int BK = GEMM_BK);
+int gemm_build_wgrad(GemmParams* gp, const Planes& At, const Planes& Bt, int M, int N, int b_row0, int b_col0, int splits, float* out,
+                     int64_t out_ld, int out_col0, int64_t split_rows, int BN);
 int gemm_launch(const GemmParams& gp, int BN, int precision, int num_sms, cudaStream_t stream);
 int gemm_max_smem_setup();
 
@@ -281,6 +286,21 @@ int campplus_embd_dim(const CamppModel* m);
 size_t campplus_workspace_bytes(const CamppModel* m, int B, int T);
 int campplus_forward(CamppModel* m, const float* feat, int B, int T, float* emb, void* ws, size_t ws_bytes, cudaStream_t st);
 int campplus_read_tap(CamppModel* m, const char* name, float* out, size_t out_elems, cudaStream_t st);
+
+// ---- ecapa_train.cu / train_kernels.cu ---------------------------------------------------------------
+struct Trainer;
+int trainer_create(const ppv_ecapa_cfg* cfg, int num_classes, Trainer** out);
+void trainer_destroy(Trainer* t);
+int64_t trainer_param_count(const Trainer* t);
+int64_t trainer_stat_count(const Trainer* t);
+int trainer_lookup(const Trainer* t, const char* name, int64_t* off, int64_t* numel, int* is_stat);
+int trainer_bind(Trainer* t, float* params, float* grads, float* stats);
+size_t trainer_workspace_bytes(Trainer* t, int B, int T);
+int trainer_forward_backward(Trainer* t, const float* feat, const int64_t* labels, int B, int T, float margin, float scale, int easy_margin,
+                             float label_smoothing, float* loss_out, float* logits_out, void* ws, size_t ws_bytes, cudaStream_t st);
+int trainer_read_tap(Trainer* t, const char* name, float* out, size_t out_elems, cudaStream_t st);
+int adam_step(float* params, const float* grads, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
+              int64_t step, float grad_scale, cudaStream_t st);
 
 // ---- cosine.cu / aam.cu -----------------------------------------------------------------------------
 size_t cosine_workspace_bytes(int M, int N, int D);

@@ -313,6 +313,7 @@ __global__ void __launch_bounds__(STAT_WARPS * 32)
             *reinterpret_cast<float2*>(out_raw + int64_t(b) * 2 * C + c) = mean;
             *reinterpret_cast<float2*>(out_raw + int64_t(b) * 2 * C + C + c) = make_float2(stdx, stdy);
         }
+        if (!bn_scale || !out_pl.base) return;  // training path: raw statistics only
         const float2 s0 = *reinterpret_cast<const float2*>(bn_scale + c), h0 = *reinterpret_cast<const float2*>(bn_shift + c);
         const float2 s1 = *reinterpret_cast<const float2*>(bn_scale + C + c),
                      h1 = *reinterpret_cast<const float2*>(bn_shift + C + c);

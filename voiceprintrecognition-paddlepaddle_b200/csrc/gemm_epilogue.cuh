@@ -89,14 +89,14 @@ __device__ __forceinline__ void epilogue_math(const Epilogue& ep, int N, int col
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const Epilogue& ep, const CUtensorMap* map_out, int M, int N, int m0, int n0,
                                               uint32_t tmem_acc, uint32_t tfull_bar, uint32_t acc_phase, uint32_t tempty_bar, int q,
-                                              int lane, int ehalf, int etid, uint32_t staging, uint8_t* staging_gen) {
+                                              int lane, int ehalf, int etid, uint32_t staging, uint8_t* staging_gen, int64_t out_row_shift = 0) {
     // row bookkeeping
     const int rloc = q * 32 + lane;  // row within the tile == TMEM lane
     const int64_t row = int64_t(m0) + rloc;
     bool valid = row < M;
     int64_t mirror_a = -1, mirror_b = -1;
     int64_t grp = 0, sgrp = 0;
-    int64_t out_row = row;
+    int64_t out_row = row + out_row_shift;  // wgrad mode: partial block of this K split
     if (ep.img_Wp > 0) {
         const int64_t img = int64_t(ep.img_Hp) * ep.img_Wp;
         grp = row / img;

@@ -115,7 +115,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     griddep_launch_dependents();  // PDL: the next kernel may begin its prologue
     griddep_wait();               // PDL: upstream activations are complete and visible
 
-    const int num_tiles = gp.m_tiles * gp.n_tiles;
+    // lin_splits > 0: "wgrad" mode -- the contraction runs over the COLUMNS of both operands (two transposed matrices
+    // [M][R] and [N][R]), k-step s of split z reads columns (z * nk + s) * BK; there is no k-step table, and split z of
+    // tile (m, n) accumulates into its own partial output block (rows shifted by z * lin_split_rows).
+    const int mn_tiles = gp.m_tiles * gp.n_tiles;
+    const int num_tiles = mn_tiles * (gp.lin_splits > 0 ? gp.lin_splits : 1);
     const int nk = gp.num_ksteps;
 
     if (warp == 0) {
@@ -123,8 +127,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m0 = (tile / gp.n_tiles) * GEMM_BM;
-            const int n0 = (tile % gp.n_tiles) * BN;
+            const int tmn = tile % mn_tiles, zsplit = tile / mn_tiles;
+            const int m0 = (tmn / gp.n_tiles) * GEMM_BM;
+            const int n0 = (tmn % gp.n_tiles) * BN;
             // L2 prefetch of the activation rows of this CTA's NEXT tile (one CTA per m-tile issues it): they come
             // from HBM, and a 2-4 slot ring alone cannot hide that latency.
             const int ntile = tile + gridDim.x;
@@ -140,18 +145,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             for (int s = 0; s < nk; ++s) {
                 mbar_wait(empty_bar(stage), phase ^ 1u);
                 if (lane == 0) {
-                    const KStep ks = gp.ksteps[s];
                     const uint32_t sa = tiles_base + stage * Cfg::STAGE_BYTES;
                     const uint32_t sb = sa + Cfg::NA * Cfg::A_BYTES;
                     const uint32_t fb = full_bar(stage);
                     mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
-                    const CUtensorMap* ma = &gp.mapA[ks.map];
+                    if (gp.lin_splits > 0) {
+                        const int kcol = (zsplit * nk + s) * BK;
 #pragma unroll
-                    for (int p = 0; p < Cfg::NA; ++p)
-                        tma_load_3d(sa + p * Cfg::A_BYTES, ma, fb, ks.a_col, m0 + ks.row_off, p);
+                        for (int p = 0; p < Cfg::NA; ++p) tma_load_3d(sa + p * Cfg::A_BYTES, &gp.mapA[0], fb, kcol, m0, p);
 #pragma unroll
-                    for (int p = 0; p < Cfg::NB; ++p)
-                        tma_load_3d(sb + p * Cfg::B_BYTES, &gp.mapB, fb, s * BK, n0, p);
+                        for (int p = 0; p < Cfg::NB; ++p)
+                            tma_load_3d(sb + p * Cfg::B_BYTES, &gp.mapB, fb, kcol + gp.lin_b_col0, gp.lin_b_row0 + n0, p);
+                    } else {
+                        const KStep ks = gp.ksteps[s];
+                        const CUtensorMap* ma = &gp.mapA[ks.map];
+#pragma unroll
+                        for (int p = 0; p < Cfg::NA; ++p)
+                            tma_load_3d(sa + p * Cfg::A_BYTES, ma, fb, ks.a_col, m0 + ks.row_off, p);
+#pragma unroll
+                        for (int p = 0; p < Cfg::NB; ++p)
+                            tma_load_3d(sb + p * Cfg::B_BYTES, &gp.mapB, fb, s * BK, n0, p);
+                    }
                 }
                 __syncwarp();
                 if (++stage == STAGES) {
@@ -211,10 +225,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m0 = (tile / gp.n_tiles) * GEMM_BM;
-            const int n0 = (tile % gp.n_tiles) * BN;
+            const int tmn = tile % mn_tiles;
+            const int m0 = (tmn / gp.n_tiles) * GEMM_BM;
+            const int n0 = (tmn % gp.n_tiles) * BN;
             epilogue_tile<BN>(gp.epi, &gp.mapOut, gp.M, gp.N, m0, n0, tmem_base + acc * BN, tfull_bar(acc), acc_phase, tempty_bar(acc), q,
-                              lane, ehalf, etid, staging, staging_gen);
+                              lane, ehalf, etid, staging, staging_gen, int64_t(tile / mn_tiles) * gp.lin_split_rows);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
         }
@@ -342,6 +357,42 @@ int gemm_build(GemmParams* gp, const GemmSource* srcs, int nsrc, const Planes& W
     return PPV_OK;
 }
 
+// Weight-gradient GEMM: out[z][m, out_col0 + n] = sum over columns r of split z of  At[m, r] * Bt[b_row0 + n, r + b_col0]
+// (At = transposed output gradient [M][R], Bt = transposed layer input [*][R]; b_col0 = conv tap offset in rows of the
+// padded time layout).  Partial blocks are `split_rows` output rows apart; the caller sums them.
+int gemm_build_wgrad(GemmParams* gp, const Planes& At, const Planes& Bt, int M, int N, int b_row0, int b_col0, int splits, float* out,
+                     int64_t out_ld, int out_col0, int64_t split_rows, int BN) {
+    PPV_REQUIRE(BN == 64 || BN == 128 || BN == 256, "gemm_build_wgrad: BN must be 64/128/256");
+    PPV_REQUIRE(At.ld == Bt.ld && splits >= 1, "gemm_build_wgrad: operands must share the contraction length");
+    memset(gp, 0, sizeof(*gp));
+    int rc = encode_planes_map_ex(&gp->mapA[0], At, GEMM_BK, GEMM_BM, 128);
+    if (rc) return rc;
+    for (int j = 1; j < GEMM_MAX_MAPS; ++j) gp->mapA[j] = gp->mapA[0];
+    rc = encode_planes_map_ex(&gp->mapB, Bt, GEMM_BK, BN, 128);
+    if (rc) return rc;
+    const int nk_total = (At.ld + GEMM_BK - 1) / GEMM_BK;
+    gp->lin_splits = std::min(splits, nk_total);
+    gp->num_ksteps = (nk_total + gp->lin_splits - 1) / gp->lin_splits;
+    gp->lin_b_row0 = b_row0;
+    gp->lin_b_col0 = b_col0;
+    gp->lin_split_rows = split_rows;
+    gp->bk = GEMM_BK;
+    gp->M = M;
+    gp->N = N;
+    gp->m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
+    gp->n_tiles = (N + BN - 1) / BN;
+    Epilogue ep;
+    ep.out_mode = OUT_F32;
+    ep.out = out;
+    ep.out_ld = out_ld;
+    ep.out_col0 = out_col0;
+    gp->epi = ep;
+    gp->epi.f32_vec_ok = ((out_ld % 4) == 0 && (out_col0 % 4) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? 1 : 0;
+    if ((out_ld % 8) == 0 && (out_col0 % 8) == 0 && (reinterpret_cast<uintptr_t>(out) & 31) == 0) gp->epi.f32_vec_ok = 2;
+    PPV_REQUIRE(N % 32 == 0, "gemm_build_wgrad: N % 32 == 0 required");
+    return PPV_OK;
+}
+
 template <int BN, int NSPLIT, int BK>
 static int launch_one(const GemmParams& gp, int num_sms, cudaStream_t stream) {
     using Cfg = GemmCfg<BN, NSPLIT, BK>;
@@ -351,7 +402,7 @@ static int launch_one(const GemmParams& gp, int num_sms, cudaStream_t stream) {
                                          Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    const int tiles = gp.m_tiles * gp.n_tiles;
+    const int tiles = gp.m_tiles * gp.n_tiles * (gp.lin_splits > 0 ? gp.lin_splits : 1);
     const int grid = std::min(tiles, num_sms);
     PPV_PDL_OK(launch_pdl(gemm_tcgen05_kernel<BN, NSPLIT, BK>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, gp),
                "gemm_tcgen05_kernel");

@@ -96,6 +96,17 @@ SIGNATURES = {
     "ppv_model_profile": (C.c_int, [_P, C.c_int]),
     "ppv_model_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64),
                                          C.POINTER(C.c_int64)]),
+    "ppv_trainer_create": (C.c_int, [C.POINTER(EcapaCfg), C.c_int, C.POINTER(_P)]),
+    "ppv_trainer_destroy": (C.c_int, [_P]),
+    "ppv_trainer_param_count": (C.c_int64, [_P]),
+    "ppv_trainer_stat_count": (C.c_int64, [_P]),
+    "ppv_trainer_lookup": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
+    "ppv_trainer_bind": (C.c_int, [_P, _P, _P, _P]),
+    "ppv_trainer_workspace_bytes": (C.c_size_t, [_P, C.c_int, C.c_int]),
+    "ppv_trainer_forward_backward": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, _P, _P, _P,
+                                               C.c_size_t, _P]),
+    "ppv_trainer_read_tap": (C.c_int, [_P, C.c_char_p, _P, C.c_size_t, _P]),
+    "ppv_adam_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, C.c_float, _P]),
     "ppv_cosine_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "ppv_cosine_matrix": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_size_t, _P]),
     "ppv_cosine_pairlist": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, _P, _P]),
