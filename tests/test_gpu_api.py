@@ -141,5 +141,40 @@ def test_trainer_extract_features_and_evaluate(cuda, wavs, cfg, W64, tmp_path):
     eer_ref, thr_ref = compute_eer(fnr, fpr, scores)
     assert abs(eer - float(eer_ref)) < 1e-6 and abs(threshold - float(thr_ref)) < 1e-4
     assert abs(min_dcf - float(compute_dcf(fnr, fpr))) < 1e-6
+
+
+def test_trainer_train_runs_the_cuda_step(cuda, wavs, cfg, tmp_path):
+    """PPVectorTrainer.train (trainer.py:281-365): list file -> features -> SpecAugment -> CUDA training step -> Adam with the
+    reference's LR / margin schedules -> checkpoint with the reference's key names -> evaluate on it."""
+    import copy
+    paths, g = wavs
+    cfg = copy.deepcopy(cfg)
+    spk = {"a_1": 0, "a_2": 0, "b_1": 1, "b_2": 1, "long3s": 2}
+    lists = {}
+    for name, members in {"train": NAMES + NAMES, "enroll": ["a_1", "b_1", "long3s"], "trials": ["a_2", "b_2"]}.items():
+        p = str(tmp_path / f"{name}_list.txt")
+        with open(p, "w") as f:
+            for n in members:
+                f.write(f"{paths[n]}\t{spk[n]}\n")
+        lists[name] = p
+    cfg["dataset_conf"]["train_list"], cfg["dataset_conf"]["enroll_list"], cfg["dataset_conf"]["trials_list"] = \
+        lists["train"], lists["enroll"], lists["trials"]
+    cfg["dataset_conf"]["sampler"]["batch_size"] = 4
+    cfg["model_conf"]["classifier"]["num_speakers"] = 3
+    cfg["train_conf"]["max_epoch"] = 2
+    cfg["train_conf"]["log_interval"] = 1
+    aug = {"spec_aug": {"prob": 0.5, "freq_mask_ratio": 0.1, "n_freq_masks": 1, "time_mask_ratio": 0.05, "n_time_masks": 1, "max_time_warp": 0},
+           "noise": {"prob": 0.0}}
+    tr = PPVectorTrainer(cfg, use_gpu=True, data_augment_configs=aug)
+    save = str(tmp_path / "models")
+    history = tr.train(save_model_path=save, do_eval=True)
+    assert len(history) == 4 and all(np.isfinite(history)) and history[0] > 0.5  # 10 utterances / batch 4, drop_last: 2 steps x 2 epochs
+    assert tr.engine.step_count == 4 and float(tr.engine.exp_avg_sq.abs().sum()) > 0
+    ck = torch.load(os.path.join(save, "model.pt"))
+    assert "0.blocks.0.conv.conv.weight" in ck and ck["1.weight"].shape == (192, 3)
+    eer, min_dcf, thr = PPVectorTrainer(cfg, use_gpu=True).evaluate(resume_model=save)
+    assert 0.0 <= eer <= 1.0 and np.isfinite(thr)
+    cfg2 = copy.deepcopy(cfg)
+    cfg2["model_conf"]["model"] = "ResNetSE"
     with pytest.raises(NotImplementedError):
-        tr.train()
+        PPVectorTrainer(cfg2, use_gpu=True).train()

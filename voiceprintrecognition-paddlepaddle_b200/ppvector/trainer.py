@@ -1,9 +1,11 @@
-"""PPVectorTrainer -- the feature-extraction and evaluation halves of ppvector/trainer.py:33-474.
+"""PPVectorTrainer -- drop-in for ppvector/trainer.py:33-474 (feature extraction, training, evaluation).
 
 ``extract_features`` (trainer.py:134-157) and ``evaluate`` (trainer.py:367-447) keep their signatures, list-file formats and
 return values; featurisation, the backbone and the trial x enrol cosine matrix run on the GPU through libppv_b200, EER /
-minDCF stay host numpy.  ``train`` needs the backward / optimizer kernels, which are not built
-yet: it raises instead of falling back to anything."""
+minDCF stay host numpy.  ``train`` (trainer.py:281-365 with the step of :206-229) runs the CUDA training step of
+``ppvector.train_engine.TrainEngine`` (train-mode forward, AAM loss, backward, one gradient all-reduce over NCCL, Adam) with the
+reference's schedules; it is implemented for EcapaTdnn + AAMLoss + Adam + WarmupCosineSchedulerLR (configs/ecapa_tdnn.yml) and
+raises for other combinations.  VisualDL logging and checkpoint rotation are out of scope: the weights are saved with torch."""
 import os
 
 import numpy as np
@@ -124,9 +126,124 @@ class PPVectorTrainer(object):
             logger.warning('save_image_path: plotting is out of scope of the B200 hot path (ignored)')
         return float(eer), float(min_dcf), float(threshold)
 
-    def train(self, *args, **kwargs):
-        raise NotImplementedError('training (backbone backward, Adam, DDP all-reduce: SURVEY.md §8 row a11) is not built yet; '
-                                  'the AAM head forward/backward is available as ppvector.loss.AAMLoss')
+    # ---- trainer.py:281-365, step :206-229 ---------------------------------------------------------------------
+    def _train_batches(self, dataset, batch_size, epoch, rank, world, shuffle=True, drop_last=True):
+        """paddle.io.DistributedBatchSampler: one permutation per epoch (seeded by the epoch), padded to a multiple of the
+        world size, rank r takes every world-th index; batches of ``batch_size`` per rank."""
+        n = len(dataset)
+        idx = np.arange(n)
+        if shuffle:
+            np.random.RandomState(epoch).shuffle(idx)
+        total = int(np.ceil(n / world)) * world
+        idx = np.concatenate([idx, idx[: total - n]])[rank::world]
+        for i in range(0, len(idx), batch_size):
+            chunk = idx[i:i + batch_size]
+            if len(chunk) < batch_size and (drop_last or len(chunk) < 2):
+                break
+            yield collate_fn([dataset[int(j)] for j in chunk])
+
+    def train(self, save_model_path='models/', log_dir='log/', resume_model=None, pretrained_model=None, do_eval=True, max_steps=None):
+        """reference: trainer.py:281-365.  ``max_steps`` (extension) stops early -- used by the tests and the bench tool."""
+        import random as _random
+
+        import torch.distributed as dist
+
+        from ppvector.loss import AAMLoss
+        from ppvector.optimizer import MarginScheduler, build_lr_scheduler
+        from ppvector.train_engine import TrainEngine
+        cf = self.configs
+        use_model = cf.model_conf.get('model', 'CAMPPlus')
+        if use_model != 'EcapaTdnn':
+            raise NotImplementedError(f'training on the B200 path is implemented for EcapaTdnn (got {use_model}); no fallback')
+        if cf.loss_conf.get('loss', 'AAMLoss') != 'AAMLoss' or cf.optimizer_conf.get('optimizer', 'Adam') != 'Adam':
+            raise NotImplementedError('training on the B200 path implements AAMLoss + Adam (configs/ecapa_tdnn.yml)')
+        if cf.train_conf.get('enable_amp', False):
+            raise NotImplementedError('enable_amp: the B200 training step runs its fp32-grade split-bf16 path only')
+        if cf.dataset_conf.get('is_use_pksampler', False):
+            raise NotImplementedError('PKSampler is out of scope of the B200 path')
+        torch.manual_seed(1000)  # trainer.py:290
+        np.random.seed(1000)
+        _random.seed(1000)
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank() if world > 1 else 0
+        fz = self._featurizer()
+        dataset_args = dict(cf.dataset_conf.get('dataset', {}))
+        train_dataset = PPVectorDataset(data_list_path=cf.dataset_conf.train_list, audio_featurizer=fz, mode='train', device=self.device,
+                                        aug_conf=self.data_augment_configs, **dataset_args)
+        sampler = cf.dataset_conf.get('sampler', {})
+        batch_size = int(sampler.get('batch_size', 64))
+        num_speakers = int(cf.model_conf.classifier.num_speakers)
+        model_args = dict(cf.model_conf.get('model_args', {}))
+        backbone = build_model(input_size=fz.feature_dim, configs=cf)  # random init with the mirror's initialisers, names = state_dict
+        engine = TrainEngine(input_size=fz.feature_dim, num_speakers=num_speakers, embd_dim=model_args.get('embd_dim', 192), device=self.device)
+        shapes = {k: tuple(v.shape) for k, v in backbone.state_dict().items()}
+        sd = {k: v for k, v in backbone.state_dict().items()}
+        cls_w = torch.empty(engine.embd_dim, num_speakers)
+        torch.nn.init.xavier_uniform_(cls_w)  # fc.py:34-36
+        for path in (pretrained_model, resume_model):
+            if path is not None:
+                loaded = load_state_dict_file(path)
+                for k, v in loaded.items():
+                    if k.startswith('1.') or k == 'classifier.weight':
+                        cls_w = torch.as_tensor(np.asarray(v))
+                    else:
+                        sd[k[2:] if k.startswith('0.') else k] = torch.as_tensor(np.asarray(v))
+        engine.load_state_dict(sd, cls_w)
+        if world > 1:  # every rank starts from rank 0's weights (fleet.distributed_model broadcasts them)
+            dist.broadcast(engine.params, src=0)
+            dist.broadcast(engine.stats, src=0)
+        steps_per_epoch = max(1, (int(np.ceil(len(train_dataset) / world)) // batch_size))
+        scheduler = build_lr_scheduler(step_per_epoch=steps_per_epoch, configs=cf)
+        loss_args = dict(cf.loss_conf.get('loss_args', {}))
+        criterion = AAMLoss(**loss_args)
+        margin_scheduler = None
+        if cf.loss_conf.get('use_margin_scheduler', False):
+            margin_scheduler = MarginScheduler(criterion=criterion, step_per_epoch=steps_per_epoch, increase_start_epoch=int(cf.train_conf.max_epoch * 0.3),
+                                               fix_epoch=int(cf.train_conf.max_epoch * 0.7), **dict(cf.loss_conf.get('margin_scheduler_args', {})))
+        wd = float(dict(cf.optimizer_conf.get('optimizer_args', {})).get('weight_decay', 0.0))
+        logger.info('训练数据：{}'.format(len(train_dataset)))
+        self.train_step, self.train_loss, self.train_acc = 0, None, None
+        history = []
+        for epoch_id in range(int(cf.train_conf.max_epoch)):
+            losses, accs = [], []
+            for features, label, _lens in self._train_batches(train_dataset, batch_size, epoch_id, rank, world, sampler.get('shuffle', True),
+                                                              sampler.get('drop_last', True)):
+                if self.stop_train or (max_steps is not None and self.train_step >= max_steps):
+                    break
+                loss, logits = engine.forward_backward(features, label, margin=criterion.margin, scale=criterion.scale,
+                                                       easy_margin=criterion.easy_margin, label_smoothing=criterion.label_smoothing,
+                                                       return_logits=True)
+                engine.adam_step(lr=scheduler.get_lr(), weight_decay=wd, grad_scale=engine.all_reduce_grads())
+                accs.append((logits.argmax(1).cpu() == label.cpu()).float().mean().item())
+                losses.append(float(loss))  # the reference syncs here too (trainer.py:237-238)
+                self.train_step += 1
+                if self.train_step % int(cf.train_conf.get('log_interval', 10)) == 0 and rank == 0:
+                    self.train_loss, self.train_acc = float(np.mean(losses)), float(np.mean(accs))
+                    logger.info(f'Train epoch: [{epoch_id}/{cf.train_conf.max_epoch}], step: {self.train_step}, loss: {self.train_loss:.5f}, '
+                                f'accuracy: {self.train_acc:.5f}, learning rate: {scheduler.get_lr():.8f}, margin: {criterion.margin}')
+                    losses, accs = [], []
+                history.append(float(loss))
+                scheduler.step()
+                if margin_scheduler:
+                    margin_scheduler.step()
+            if self.stop_train or (max_steps is not None and self.train_step >= max_steps):
+                break
+            if world > 1:
+                dist.barrier()  # the reference lets rank 0 evaluate while the others run ahead; keep the ranks together
+            if rank == 0:
+                self._state_dict = {k: v.cpu().numpy() for k, v in engine.state_dict(shapes).items()}
+                os.makedirs(save_model_path, exist_ok=True)
+                # keys as in the reference's Sequential(backbone, classifier) checkpoint: "0.<backbone tensor>", "1.weight"
+                ckpt = {'0.' + k: torch.from_numpy(v) for k, v in self._state_dict.items()}
+                ckpt['1.weight'] = engine.view('classifier.weight', (engine.embd_dim, num_speakers)).detach().cpu().clone()
+                torch.save(ckpt, os.path.join(save_model_path, 'model.pt'))
+                if do_eval and os.path.exists(cf.dataset_conf.enroll_list):
+                    self.model = None
+                    eer, min_dcf, threshold = self.evaluate()
+                    logger.info(f'Test epoch: {epoch_id}, threshold: {threshold:.2f}, EER: {eer:.5f}, MinDCF: {min_dcf:.5f}')
+        self._state_dict = {k: v.cpu().numpy() for k, v in engine.state_dict(shapes).items()}
+        self.engine = engine
+        return history
 
     def export(self, *args, **kwargs):
         raise NotImplementedError('export is broken in the reference (trainer.py:467-469) and out of scope')
