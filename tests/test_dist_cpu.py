@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from ppvector.parallel import gather_rows, max_over_ranks, shard_range, sharded_score_rows
+from ppvector.parallel import allreduce_flat_grads, gather_rows, max_over_ranks, shard_range, sharded_score_rows, train_sample_indices
 
 
 def test_shard_range_partitions():
@@ -42,9 +42,13 @@ def _worker(rank, world, port, out_path):
     rows = torch.arange(b, e, dtype=torch.float32)[:, None].repeat(1, 3)
     gathered = gather_rows(rows, 13)
     t = max_over_ranks(1.0 + rank, torch.device("cpu"))
+    # training: one all-reduce over the flat gradient buffer, then the same optimizer step on every rank
+    grads = torch.arange(10, dtype=torch.float32) * (rank + 1)
+    scale = allreduce_flat_grads(grads)
+    idx = train_sample_indices(7, 3, rank, world)
     if rank == 0:
         np.savez(out_path, full=full.numpy(), gathered=gathered.numpy(), t=t,
-                 ref=oh.cosine_matrix(trials.numpy(), enroll.numpy()))
+                 ref=oh.cosine_matrix(trials.numpy(), enroll.numpy()), grads=grads.numpy(), scale=scale, idx=idx)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -56,3 +60,15 @@ def test_two_rank_gloo(tmp_path):
     assert np.abs(z["full"] - z["ref"]).max() < 1e-6
     assert np.array_equal(z["gathered"][:, 0], np.arange(13, dtype=np.float32))
     assert float(z["t"]) == 2.0  # max over ranks
+    assert np.array_equal(z["grads"], np.arange(10, dtype=np.float32) * 3) and float(z["scale"]) == 0.5
+    assert len(z["idx"]) == 4
+
+
+def test_train_sample_indices_cover_the_epoch():
+    for n, world in ((7, 2), (10, 3), (64, 8)):
+        parts = [train_sample_indices(n, 5, r, world) for r in range(world)]
+        assert len({len(p) for p in parts}) == 1  # every rank sees the same number of samples
+        assert set(np.concatenate(parts).tolist()) == set(range(n))
+        assert not np.array_equal(np.sort(parts[0]), parts[0]) or n < 3  # shuffled
+    assert np.array_equal(train_sample_indices(5, 0, 0, 1, shuffle=False), np.arange(5))
+    assert allreduce_flat_grads(torch.ones(3)) == 1.0  # no process group: identity

@@ -71,6 +71,8 @@ def main():
                           "batch_per_gpu": a.batch, "frames": a.frames, "speakers": a.speakers, "loss": float(loss),
                           "algorithmic_tflops": round(world * a.batch * 3 * 2.857e9 / (ms * 1e-3) / 1e12, 1),
                           "workspace_GB": round(eng._ws.numel() / 2**30, 2)}))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

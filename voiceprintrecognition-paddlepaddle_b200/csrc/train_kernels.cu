@@ -160,23 +160,37 @@ __global__ void __launch_bounds__(TR_WARPS * 32) bn_stats_kernel(Planes a, int c
         p[2 * C] = K;
     }
 }
-// combine the per-utterance partials (Chan et al.) in double; y = a * scale + shift with scale = gamma * rstd
-__global__ void bn_stats_finalize_kernel(const float* __restrict__ part, int B, int C, int T, float eps, float momentum, const float* __restrict__ gamma,
-                                         const float* __restrict__ beta, float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                                         float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ run_mean, float* __restrict__ run_var) {
-    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+// combine the per-utterance partials in double (all utterances hold T frames: mean = avg of the utterance means,
+// M2 = sum M2_b + T * sum (mean_b - mean)^2); one warp per channel, lanes stride over the utterances, fixed reduction order.
+// y = a * scale + shift with scale = gamma * rstd
+__global__ void __launch_bounds__(256)
+    bn_stats_finalize_kernel(const float* __restrict__ part, int B, int C, int T, float eps, float momentum, const float* __restrict__ gamma,
+                             const float* __restrict__ beta, float* __restrict__ mean_out, float* __restrict__ rstd_out, float* __restrict__ scale,
+                             float* __restrict__ shift, float* __restrict__ run_mean, float* __restrict__ run_var) {
+    const int ch = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (ch >= C) return;
-    double n = 0.0, mean = 0.0, M2 = 0.0;
-    for (int b = 0; b < B; ++b) {
+    const double nb = T;
+    double sm = 0.0, sm2 = 0.0;
+    for (int b = lane; b < B; b += 32) {
         const float* p = part + (int64_t(b) * 3) * C + ch;
         const double S = p[0], Q = p[C], K = p[2 * C];
-        const double nb = T, mb = K + S / nb, M2b = Q - S * S / nb;
-        const double d = mb - mean, nt = n + nb;
-        mean += d * nb / nt;
-        M2 += M2b + d * d * n * nb / nt;
-        n = nt;
+        sm += K + S / nb;
+        sm2 += Q - S * S / nb;
     }
-    const double var = fmax(M2 / n, 0.0);  // biased, as used for the normalisation
+    for (int o = 16; o > 0; o >>= 1) {
+        sm += __shfl_xor_sync(0xffffffffu, sm, o);
+        sm2 += __shfl_xor_sync(0xffffffffu, sm2, o);
+    }
+    const double mean = sm / B;
+    double sd = 0.0;
+    for (int b = lane; b < B; b += 32) {
+        const float* p = part + (int64_t(b) * 3) * C + ch;
+        const double d = double(p[2 * C]) + double(p[0]) / nb - mean;
+        sd += d * d;
+    }
+    for (int o = 16; o > 0; o >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, o);
+    if (lane != 0) return;
+    const double var = fmax((sm2 + nb * sd) / (nb * B), 0.0);  // biased, as used for the normalisation
     const float rstd = float(1.0 / sqrt(var + double(eps)));
     mean_out[ch] = float(mean);
     rstd_out[ch] = rstd;
@@ -258,15 +272,20 @@ __global__ void __launch_bounds__(TR_WARPS * 32)
         part[(int64_t(b) * 2 + 1) * C + ch] = out[1];
     }
 }
-// out0[c] = sum_b part[b][0][c] (-> d beta), out1[c] = sum_b part[b][1][c] (-> d gamma); nq = 1 or 2
-__global__ void part_finalize_kernel(const float* __restrict__ part, int B, int C, int nq, float* __restrict__ out0, float* __restrict__ out1) {
-    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+// out0[c] = sum_b part[b][0][c] (-> d beta), out1[c] = sum_b part[b][1][c] (-> d gamma); nq = 1 or 2.  One warp per channel.
+__global__ void __launch_bounds__(256) part_finalize_kernel(const float* __restrict__ part, int B, int C, int nq, float* __restrict__ out0, float* __restrict__ out1) {
+    const int ch = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (ch >= C) return;
     float a0 = 0.f, a1 = 0.f;
-    for (int b = 0; b < B; ++b) {
+    for (int b = lane; b < B; b += 32) {
         a0 += part[(int64_t(b) * nq) * C + ch];
         if (nq == 2) a1 += part[(int64_t(b) * nq + 1) * C + ch];
     }
+    for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    }
+    if (lane != 0) return;
     out0[ch] = a0;
     if (nq == 2 && out1) out1[ch] = a1;
 }
@@ -602,7 +621,7 @@ int tr_bn_forward(const Planes& a, int a_col0, int C, int B, int T, int P, int T
     PPV_REQUIRE(C % 64 == 0 && a_col0 % 8 == 0, "bn_forward: C % 64 == 0 required");
     bn_stats_kernel<<<dim3(C / 64, B), TR_WARPS * 32, 0, st>>>(a, a_col0, C, T, P, Tp, part);
     TR_LAUNCH_OK("bn_stats_kernel");
-    bn_stats_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, B, C, T, eps, momentum, gamma, beta, mean, rstd, scale, shift, run_mean, run_var);
+    bn_stats_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(part, B, C, T, eps, momentum, gamma, beta, mean, rstd, scale, shift, run_mean, run_var);
     TR_LAUNCH_OK("bn_stats_finalize_kernel");
     BnApplyArgs p = apply_in;
     p.a = a;
@@ -625,13 +644,13 @@ int tr_bn_backward(const GradSrcList& gl, const Planes& a, int a_col0, int C, in
     PPV_REQUIRE(C % 64 == 0, "bn_backward: C % 64 == 0 required");
     bn_bwd_reduce_kernel<<<dim3(C / 64, B), TR_WARPS * 32, 0, st>>>(gl, a, a_col0, C, T, P, Tp, mean, rstd, part);
     TR_LAUNCH_OK("bn_bwd_reduce_kernel");
-    part_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, B, C, 2, dbeta, dgamma);
+    part_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(part, B, C, 2, dbeta, dgamma);
     TR_LAUNCH_OK("part_finalize_kernel");
     bn_bwd_apply_kernel<<<dim3(C / 64, B), TR_WARPS * 32, 0, st>>>(gl, a, a_col0, C, T, P, Tp, mean, rstd, gamma, dbeta, dgamma,
                                                                   1.f / (float(B) * float(T)), dz, dz_col0, part);
     TR_LAUNCH_OK("bn_bwd_apply_kernel");
     if (dbias) {
-        part_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, B, C, 1, dbias, nullptr);
+        part_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(part, B, C, 1, dbias, nullptr);
         TR_LAUNCH_OK("part_finalize_kernel");
     }
     return PPV_OK;
@@ -642,7 +661,7 @@ int tr_grad_sum(const GradSrcList& gl, int C, int B, int T, int P, int Tp, const
     grad_sum_kernel<<<dim3(C / 64, B), TR_WARPS * 32, 0, st>>>(gl, C, T, P, Tp, out, out_col0, part);
     TR_LAUNCH_OK("grad_sum_kernel");
     if (colsum) {
-        part_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(part, B, C, 1, colsum, nullptr);
+        part_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(part, B, C, 1, colsum, nullptr);
         TR_LAUNCH_OK("part_finalize_kernel");
     }
     return PPV_OK;

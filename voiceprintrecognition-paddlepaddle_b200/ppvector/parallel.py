@@ -48,3 +48,23 @@ def sharded_score_rows(trial_emb: torch.Tensor, enroll_emb: torch.Tensor, score_
     b, e = shard_range(trial_emb.shape[0], rank, world)
     local = score_fn(trial_emb[b:e], enroll_emb) if e > b else trial_emb.new_zeros((0, enroll_emb.shape[0]))
     return gather_rows(local, trial_emb.shape[0])
+
+
+def allreduce_flat_grads(grads: torch.Tensor) -> float:
+    """Training: ONE all-reduce(sum) over the flat gradient buffer, in place; returns the factor the optimizer must
+    apply to the summed gradient (1 / world size) -- the reference's fleet.distributed_model averaging (trainer.py:318-320)."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+        return 1.0
+    dist.all_reduce(grads, op=dist.ReduceOp.SUM)
+    return 1.0 / dist.get_world_size()
+
+
+def train_sample_indices(n: int, epoch: int, rank: int, world: int, shuffle: bool = True):
+    """paddle.io.DistributedBatchSampler's index stream: one permutation per epoch (seeded by the epoch, identical on every rank),
+    padded by wrapping to a multiple of the world size, rank r takes every world-th index."""
+    import numpy as np
+    idx = np.arange(n)
+    if shuffle:
+        np.random.RandomState(epoch).shuffle(idx)
+    total = -(-n // world) * world
+    return np.concatenate([idx, idx[: total - n]])[rank::world]

@@ -104,11 +104,8 @@ class TrainEngine:
 
     def all_reduce_grads(self):
         """One collective over the flat gradient buffer; returns the scale ppv_adam_step must apply (1 / world size)."""
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM)
-            return 1.0 / dist.get_world_size()
-        return 1.0
+        from ppvector.parallel import allreduce_flat_grads
+        return allreduce_flat_grads(self.grads)
 
     def adam_step(self, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-6, grad_scale=1.0):
         self.step_count += 1

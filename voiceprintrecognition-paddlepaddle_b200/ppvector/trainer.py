@@ -130,12 +130,8 @@ class PPVectorTrainer(object):
     def _train_batches(self, dataset, batch_size, epoch, rank, world, shuffle=True, drop_last=True):
         """paddle.io.DistributedBatchSampler: one permutation per epoch (seeded by the epoch), padded to a multiple of the
         world size, rank r takes every world-th index; batches of ``batch_size`` per rank."""
-        n = len(dataset)
-        idx = np.arange(n)
-        if shuffle:
-            np.random.RandomState(epoch).shuffle(idx)
-        total = int(np.ceil(n / world)) * world
-        idx = np.concatenate([idx, idx[: total - n]])[rank::world]
+        from ppvector.parallel import train_sample_indices
+        idx = train_sample_indices(len(dataset), epoch, rank, world, shuffle)
         for i in range(0, len(idx), batch_size):
             chunk = idx[i:i + batch_size]
             if len(chunk) < batch_size and (drop_last or len(chunk) < 2):
