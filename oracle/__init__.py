@@ -1,8 +1,9 @@
 """CPU oracle for the ppvector speaker-embedding hot path.  TEST INFRASTRUCTURE ONLY.
 
 This package restates, on the CPU (numpy / torch fp32+fp64), the arithmetic of the
-reference hot path  waveform -> Kaldi Fbank-80 + CMN -> ECAPA-TDNN -> ASP -> 192-d
-embedding -> {AAMLoss | cosine scoring}.  It exists so that the CUDA path can be
+reference hot path  waveform -> Kaldi Fbank-80 + CMN (or an STFT front end) -> ECAPA-TDNN /
+ResNetSE / ERes2Net / CAM++ -> pooling -> 192-d embedding -> {AAMLoss | cosine scoring}, and of the
+training step around it (train-mode BatchNorm, autograd backward, Adam).  It exists so that the CUDA path can be
 checked against something; it is NOT part of the product:
 
   * only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
