@@ -169,6 +169,26 @@ struct Res2Params {
 int res2conv_build(Res2Params* rp, const GemmSource* srcs, int nsrc, const Planes& W, int M, int dil, const Epilogue& epi);
 int res2conv_launch(const Res2Params& rp, int precision, int num_sms, cudaStream_t st);
 
+// ---- the whole Res2Net chain of a block, one utterance per CTA, operands resident in shared memory (res2chain.cu) ----------
+constexpr int RES2CHAIN_MAX = 7;
+struct Res2ChainParams {
+    CUtensorMap mapX;                  // tdnn1 output planes, box {64, 200, 1} (the resident tile of conv 1)
+    CUtensorMap mapXt, mapY, mapYtail; // 128-row staging tiles: next-chunk load, y store, y store of the utterance's last tile
+    CUtensorMap mapW[RES2CHAIN_MAX];   // per-conv weight planes [2][>=64][>=192], box {64, 64, 1}
+    const float* bias[RES2CHAIN_MAX];
+    const float* bn_scale[RES2CHAIN_MAX];
+    const float* bn_shift[RES2CHAIN_MAX];
+    Planes x;  // tdnn1 output [rows][>= 8*64]: chunk j at columns 64 j
+    Planes y;  // Res2Net output [rows][>= 8*64]: conv j (1-based) -> columns 64 j
+    int nconv, width, B, T, P, Tp, dil, ntiles;
+    unsigned long long* trace;  // debug (PPV_RES2_TRACE): clock64 stamps of CTA 0's first utterance, [role][conv][event]
+};
+int res2chain_build(Res2ChainParams* cp, const Planes& x, const Planes& y, const Planes* W, const float* const* bias, const float* const* bn_scale,
+                    const float* const* bn_shift, int nconv, int B, int T, int P, int Tp, int dil);
+int res2chain_launch(const Res2ChainParams& cp, int precision, int num_sms, cudaStream_t st);
+bool res2chain_fits(int T, int P);
+void res2chain_trace_dump(const Res2ChainParams& cp);
+
 // ---- fused attentive statistics pooling (asp_fused.cu) ----------------------------------------------
 struct AspFusedParams {
     CUtensorMap mapW;    // planes [2][C][K]   box {64, 128, 1}

@@ -46,10 +46,11 @@ struct KSpec {  // one K group: `ncols` columns of a source at a row offset <- w
 enum Buf { B_FEAT, B_X0, B_H, B_Y, B_Z, B_CAT, B_MFA, B_ATT, B_GSTAT, B_POOL, B_SEM, B_SEH, B_COUNT };
 
 struct Step {
-    enum Kind { GEMM, RES2, SE_SQUEEZE, SE_SCALE, ASP_GLOBAL, ASP_FUSED } kind;
+    enum Kind { GEMM, RES2, RES2CHAIN, SE_SQUEEZE, SE_SCALE, ASP_GLOBAL, ASP_FUSED } kind;
     GemmParams gp;
     AspFusedParams ap;
     Res2Params rp;
+    Res2ChainParams cp;
     int BN = 0;
     int blk = 0;  // block index for the SE steps
 };
@@ -403,6 +404,8 @@ static int build_plan(EcapaModel* m, int B, int T, void* ws, size_t ws_bytes, cu
     const int64_t R = int64_t(B) * Tp;
     const char* r2env = getenv("PPV_RES2_GEMM");  // debugging aid: 1 = run the Res2Net convs through the generic gather-GEMM
     const bool use_res2_kernel = (w == 64) && !(r2env && r2env[0] == '1');
+    const char* rcenv = getenv("PPV_RES2_CHAIN");  // 0 = one launch per Res2Net conv (res2conv.cu) instead of the fused chain
+    const bool use_res2_chain = use_res2_kernel && m->scale == 8 && res2chain_fits(T, P) && !(rcenv && rcenv[0] == '0');
     const char* bkenv = getenv("PPV_GEMM_BK32");  // experiment: 1 = 32-wide k-steps (SWIZZLE_64B) on the wide-N layers; measured slower
     const bool bk32_enabled = (bkenv && bkenv[0] == '1');
 
@@ -456,9 +459,26 @@ static int build_plan(EcapaModel* m, int B, int T, void* ws, size_t ws_bytes, cu
     for (int b = 1; b <= 3; ++b) {
         const Planes& X = (b == 1) ? m->bufs[B_X0] : m->bufs[B_CAT];
         const int xcol = (b == 1) ? 0 : (b - 2) * C;
-        rc = add_gemm(m->tdnn1[b - 1], {{-1, 0, C, 0, 0, C, 0}}, &X, xcol, int(R), planes_out(m->bufs[B_H], 0, true));
+        // the fused Res2Net chain builds the reflect halo rows itself, so tdnn1 may use the faster halo-free TMA-store epilogue
+        rc = add_gemm(m->tdnn1[b - 1], {{-1, 0, C, 0, 0, C, 0}}, &X, xcol, int(R), planes_out(m->bufs[B_H], 0, !use_res2_chain));
         if (rc) return rc;
-        for (int j = 1; j < m->scale; ++j) {
+        if (use_res2_chain) {  // all seven convs in one kernel, one utterance per CTA, operands resident in shared memory (res2chain.cu)
+            Planes Wj[RES2CHAIN_MAX];
+            const float *bj[RES2CHAIN_MAX], *sj[RES2CHAIN_MAX], *hj[RES2CHAIN_MAX];
+            for (int j = 1; j < m->scale; ++j) {
+                const ConvW& cw = m->res2[b - 1][j];
+                Wj[j - 1] = cw.W;  // the first 3 x 64 columns are the taps of source 0; source 1 repeats the same weights
+                bj[j - 1] = cw.bias;
+                sj[j - 1] = cw.bn_scale;
+                hj[j - 1] = cw.bn_shift;
+            }
+            Step stp;
+            stp.kind = Step::RES2CHAIN;
+            rc = res2chain_build(&stp.cp, m->bufs[B_H], m->bufs[B_Y], Wj, bj, sj, hj, m->scale - 1, B, T, P, Tp, m->cfg.dilations[b]);
+            if (rc) return rc;
+            m->steps.push_back(stp);
+        }
+        for (int j = 1; j < m->scale && !use_res2_chain; ++j) {
             if (use_res2_kernel) {  // weight-stationary kernel, one tall tile per source (res2conv.cu)
                 GemmSource srcs[2];
                 srcs[0] = GemmSource{m->bufs[B_H], j * w, w, 0};
@@ -602,12 +622,19 @@ int ecapa_forward(EcapaModel* m, const float* feat, Fbank* fb, const float* wav,
     prof_mark(1, false);
     if (rc) return rc;
     for (const Step& s : m->steps) {
-        const bool tensor_step = (s.kind == Step::GEMM || s.kind == Step::ASP_FUSED || s.kind == Step::RES2);
+        const bool tensor_step = (s.kind == Step::GEMM || s.kind == Step::ASP_FUSED || s.kind == Step::RES2 || s.kind == Step::RES2CHAIN);
         prof_mark(tensor_step ? 0 : 1, true);
         if (tensor_step) m->launches_gemm += 1; else m->launches_other += 1;
         switch (s.kind) {
             case Step::GEMM: rc = gemm_launch(s.gp, s.BN, m->precision, m->num_sms, st); break;
             case Step::RES2: rc = res2conv_launch(s.rp, m->precision, m->num_sms, st); break;
+            case Step::RES2CHAIN:
+                rc = res2chain_launch(s.cp, m->precision, m->num_sms, st);
+                if (s.cp.trace) {
+                    static int dumps = 0;
+                    if (++dumps == 10) res2chain_trace_dump(s.cp);  // a warm launch of the first block
+                }
+                break;
             case Step::SE_SQUEEZE:
                 rc = launch_colstats(m->bufs[B_Z], 0, C, B, T, P, Tp, 0, 0.f, nullptr, m->bufs[B_SEM], st);
                 break;
