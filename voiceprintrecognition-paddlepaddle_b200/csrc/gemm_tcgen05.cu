@@ -331,7 +331,10 @@ int gemm_build(GemmParams* gp, const GemmSource* srcs, int nsrc, const Planes& W
         const char* pf = getenv("PPV_GEMM_NO_L2PREFETCH");
         gp->l2_prefetch = (pf && pf[0] == '1') ? 0 : 1;
     }
-    if (epi.out_mode == OUT_PLANES && !epi.halo && (N % 64) == 0 && epi.img_Wp == 0) {
+    // Image-mode outputs on the SAME grid as the input (stride 1) can also go through the TMA-store staging tile: the rows that
+    // are not interior positions are the zero border of the image and are stored as zeros (which is what they must hold).
+    const bool img_same_grid = epi.img_Wp > 0 && epi.img_stride == 1 && epi.img_stride_w <= 1 && epi.out_Hp == epi.img_Hp && epi.out_Wp == epi.img_Wp;
+    if (epi.out_mode == OUT_PLANES && !epi.halo && (N % 64) == 0 && (epi.img_Wp == 0 || img_same_grid)) {
         const char* nt = getenv("PPV_GEMM_NO_TMASTORE");
         if (!(nt && nt[0] == '1')) {
             Planes po;
@@ -343,6 +346,7 @@ int gemm_build(GemmParams* gp, const GemmSource* srcs, int nsrc, const Planes& W
                 rc = encode_planes_map_ex(&gp->mapOut, po, 64, GEMM_BM, 128);
                 if (rc) return rc;
                 gp->epi.tma_store = 1;
+                if (img_same_grid) gp->epi.zero_invalid = 1;
             }
         }
     }
