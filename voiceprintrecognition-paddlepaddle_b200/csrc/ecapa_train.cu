@@ -70,7 +70,8 @@ struct TStep {
         Planes in;
         int col0, C, row0;  // row0: first row of the transposed buffer to write
         int which;          // 0 = TA, 1 = TB
-        int shift = 0;      // row shift of the input (conv tap)
+        int shift = 0;      // row shift of the input (first conv tap)
+        int ntaps = 1, shift_step = 0, row_step = 0;  // all taps of a conv in one launch
     };
     std::vector<Tr> trs;
     int layer = -1;
@@ -447,8 +448,13 @@ static int tr_build_plan(Trainer* t, int B, int T, void* ws, size_t ws_bytes, cu
         s.kind = TStep::WGRAD;
         s.layer = layer;
         s.trs.push_back(TStep::Tr{dz, dz_col0, c.Cout, 0, 0, 0});
-        for (int tp = 0; tp < c.taps; ++tp)
-            for (const TStep::Tr& x : xs) s.trs.push_back(TStep::Tr{x.in, x.col0, x.C, x.row0 + tp * c.Cinp, 1, (tp - (c.taps - 1) / 2) * c.dil});
+        for (const TStep::Tr& x : xs) {
+            TStep::Tr tr{x.in, x.col0, x.C, x.row0, 1, -((c.taps - 1) / 2) * c.dil};
+            tr.ntaps = c.taps;
+            tr.shift_step = c.dil;
+            tr.row_step = c.Cinp;
+            s.trs.push_back(tr);
+        }
         const int N = c.taps * c.Cinp;
         const int BNw = pick_bn(N);
         const int mt = (c.Cout + 127) / 128, nt = (N + BNw - 1) / BNw;
@@ -786,8 +792,11 @@ int trainer_forward_backward(Trainer* t, const float* feat, const int64_t* label
             case TStep::GRAD_SUM: rc = tr_grad_sum(s.gl, s.C, B, T, P, Tp, s.p0, s.c0, t->part, nullptr, st); break;
             case TStep::BN_BWD: {
                 const TLayer& l = t->L[s.layer];
+                // narrow layers: split the frames of an utterance over several CTAs (the attention TDNN keeps per-utterance sums)
+                const int ctas = (l.bn.C / 64) * B;
+                const int tsplit = (s.layer == t->l_att1 || ctas >= 2 * t->num_sms) ? 1 : std::min(8, std::max(1, (2 * t->num_sms + ctas - 1) / ctas));
                 rc = tr_bn_backward(s.gl, s.p0, s.c0, l.bn.C, B, T, P, Tp, l.bn.mean, l.bn.rstd, par + l.bn.g_off, grd + l.bn.g_off, grd + l.bn.b_off,
-                                    s.p1, s.c1, grd + l.conv.b_off, t->part, st);
+                                    s.p1, s.c1, grd + l.conv.b_off, t->part, st, tsplit);
                 break;
             }
             case TStep::ASP_CTX_BWD: {
@@ -823,7 +832,7 @@ int trainer_forward_backward(Trainer* t, const float* feat, const int64_t* label
                     Planes dst = tr.which == 0 ? t->TA : t->TB;
                     dst.base += int64_t(tr.row0) * dst.ld;
                     dst.rows -= tr.row0;
-                    rc = tr_transpose(tr.in, tr.col0, tr.C, t->R, dst, tr.shift, st);
+                    rc = tr_transpose(tr.in, tr.col0, tr.C, t->R, dst, tr.shift, st, tr.ntaps, tr.shift_step, tr.row_step);
                     if (rc) return rc;
                 }
                 for (const GemmParams& gp : s.wg) {

@@ -39,13 +39,16 @@ int tr_bn_forward(const Planes& a, int a_col0, int C, int B, int T, int P, int T
                   int num_sms, cudaStream_t st);
 // dz (valid frames) = d(conv output) through BatchNorm(train) and ReLU; dgamma / dbeta / dbias are [C] outputs
 int tr_bn_backward(const GradSrcList& gl, const Planes& a, int a_col0, int C, int B, int T, int P, int Tp, const float* mean, const float* rstd,
-                   const float* gamma, float* dgamma, float* dbeta, const Planes& dz, int dz_col0, float* dbias, float* part, cudaStream_t st);
+                   const float* gamma, float* dgamma, float* dbeta, const Planes& dz, int dz_col0, float* dbias, float* part, cudaStream_t st,
+                   int tsplit = 1);  // tsplit > 1: `part` holds B * tsplit partial rows (no per-utterance sums)
 // out (optional planes, valid frames) = summed sources; part [B][C] = per-utterance column sums; colsum (optional) [C]
 int tr_grad_sum(const GradSrcList& gl, int C, int B, int T, int P, int Tp, const Planes& out, int out_col0, float* part, float* colsum, cudaStream_t st);
 // out_bc [B][C] = sum_t grad(b,t,c) * y[b,t,c]
 int tr_grad_dot(const GradSrcList& gl, const Planes& y, int y_col0, int C, int B, int T, int P, int Tp, float* out_bc, cudaStream_t st);
 // out[c][r] = in[r + shift][col0 + c] (zero outside the input rows)
-int tr_transpose(const Planes& in, int col0, int C, int64_t rows, const Planes& out, int shift, cudaStream_t st);
+// ntaps > 1: tap z uses shift + z * shift_step and writes output rows [z * out_row_step, ...)  (one launch for all conv taps)
+int tr_transpose(const Planes& in, int col0, int C, int64_t rows, const Planes& out, int shift, cudaStream_t st, int ntaps = 1, int shift_step = 0,
+                 int64_t out_row_step = 0);
 // w: reference conv weight, element (n, cin, tap) at w[n * w_ld + cin * taps + tap]
 int tr_repack_conv(const float* w, int64_t w_ld, int Cout, int Cin, int Cinp, int taps, const Planes& wf, const Planes& wd, cudaStream_t st);
 int tr_wgrad_unpack(const float* part, int splits, int64_t split_rows, int Cout, int Cin, int Cinp, int taps, float* grad, int64_t g_ld,

@@ -246,7 +246,10 @@ __global__ void __launch_bounds__(TR_WARPS * 32)
     bn_bwd_reduce_kernel(GradSrcList gl, Planes a, int a_col0, int C, int T, int P, int Tp, const float* __restrict__ mean,
                          const float* __restrict__ rstd, float* __restrict__ part) {
     __shared__ float s_buf[2][TR_WARPS][64];
+    // blockIdx.z splits the frames of an utterance (narrow layers would otherwise fill only B CTAs); partial index = b * nz + z
     const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, cg = lane & 7, rsub = lane >> 3;
+    const int tchunk = (T + gridDim.z - 1) / gridDim.z, t_lo = blockIdx.z * tchunk, t_hi = min(T, t_lo + tchunk);
+    const int pb = b * gridDim.z + blockIdx.z;
     const int c = blockIdx.x * 64 + cg * 8;
     const int64_t row0 = int64_t(b) * Tp + P;
     float mu[8], rs[8], q[2][8];
@@ -254,7 +257,7 @@ __global__ void __launch_bounds__(TR_WARPS * 32)
     tr_ld8f(rstd + c, rs);
 #pragma unroll
     for (int i = 0; i < 8; ++i) q[0][i] = q[1][i] = 0.f;
-    for (int t = warp * 4 + rsub; t < T; t += TR_WARPS * 4) {
+    for (int t = t_lo + warp * 4 + rsub; t < t_hi; t += TR_WARPS * 4) {
         float g[8], v[8];
         tr_load_grad8(gl, b, t, T, P, Tp, c, g);
         tr_load8(a, row0 + t, a_col0 + c, v);
@@ -268,8 +271,8 @@ __global__ void __launch_bounds__(TR_WARPS * 32)
     tr_block_reduce<2>(q, s_buf, warp, lane, out);
     if (threadIdx.x < 64) {
         const int ch = blockIdx.x * 64 + threadIdx.x;
-        part[(int64_t(b) * 2) * C + ch] = out[0];
-        part[(int64_t(b) * 2 + 1) * C + ch] = out[1];
+        part[(int64_t(pb) * 2) * C + ch] = out[0];
+        part[(int64_t(pb) * 2 + 1) * C + ch] = out[1];
     }
 }
 // out0[c] = sum_b part[b][0][c] (-> d beta), out1[c] = sum_b part[b][1][c] (-> d gamma); nq = 1 or 2.  One warp per channel.
@@ -297,6 +300,8 @@ __global__ void __launch_bounds__(TR_WARPS * 32)
                         int dz_col0, float* __restrict__ part) {
     __shared__ float s_buf[1][TR_WARPS][64];
     const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, cg = lane & 7, rsub = lane >> 3;
+    const int tchunk = (T + gridDim.z - 1) / gridDim.z, t_lo = blockIdx.z * tchunk, t_hi = min(T, t_lo + tchunk);
+    const int pb = b * gridDim.z + blockIdx.z;
     const int c = blockIdx.x * 64 + cg * 8;
     const int64_t row0 = int64_t(b) * Tp + P;
     float mu[8], rs[8], ga[8], db[8], dg[8], q[1][8];
@@ -307,7 +312,7 @@ __global__ void __launch_bounds__(TR_WARPS * 32)
     tr_ld8f(dgamma + c, dg);
 #pragma unroll
     for (int i = 0; i < 8; ++i) q[0][i] = 0.f;
-    for (int t = warp * 4 + rsub; t < T; t += TR_WARPS * 4) {
+    for (int t = t_lo + warp * 4 + rsub; t < t_hi; t += TR_WARPS * 4) {
         float g[8], v[8], o[8];
         tr_load_grad8(gl, b, t, T, P, Tp, c, g);
         tr_load8(a, row0 + t, a_col0 + c, v);
@@ -322,7 +327,7 @@ __global__ void __launch_bounds__(TR_WARPS * 32)
     }
     float out[1];
     tr_block_reduce<1>(q, s_buf, warp, lane, out);
-    if (threadIdx.x < 64) part[int64_t(b) * C + blockIdx.x * 64 + threadIdx.x] = out[0];
+    if (threadIdx.x < 64) part[int64_t(pb) * C + blockIdx.x * 64 + threadIdx.x] = out[0];
 }
 
 // per-utterance column sums of the summed sources: part[b][c] = sum_t grad(b, t, c); optionally also writes the summed
@@ -374,8 +379,12 @@ __global__ void __launch_bounds__(TR_WARPS * 32)
 // planes [rows][ld] columns [col0, col0+C) -> planes [C][out.ld] (out.ld >= rows): out[c][r] = in[r + shift][col0 + c], zero
 // where r + shift falls outside [0, rows); 32 x 32 tiles, both planes.  (A conv tap of the weight-gradient GEMM is a row shift
 // of the layer input: TMA cannot start a tile at an inner coordinate that is not 16-byte aligned, so the shift is applied here.)
-__global__ void __launch_bounds__(256) transpose_planes_kernel(Planes in, int col0, int C, int64_t rows, Planes out, int shift) {
+__global__ void __launch_bounds__(256) transpose_planes_kernel(Planes in, int col0, int C, int64_t rows, Planes out, int shift0, int shift_step,
+                                                               int64_t out_row_step) {
     __shared__ __nv_bfloat16 tile[2][32][33];
+    // blockIdx.z = conv tap: shift = shift0 + z * shift_step, output rows start at z * out_row_step
+    const int shift = shift0 + int(blockIdx.z) * shift_step;
+    out.base += int64_t(blockIdx.z) * out_row_step * out.ld;
     const int64_t r0 = int64_t(blockIdx.x) * 32;
     const int c0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -640,17 +649,18 @@ int tr_bn_forward(const Planes& a, int a_col0, int C, int B, int T, int P, int T
 }
 
 int tr_bn_backward(const GradSrcList& gl, const Planes& a, int a_col0, int C, int B, int T, int P, int Tp, const float* mean, const float* rstd,
-                   const float* gamma, float* dgamma, float* dbeta, const Planes& dz, int dz_col0, float* dbias, float* part, cudaStream_t st) {
-    PPV_REQUIRE(C % 64 == 0, "bn_backward: C % 64 == 0 required");
-    bn_bwd_reduce_kernel<<<dim3(C / 64, B), TR_WARPS * 32, 0, st>>>(gl, a, a_col0, C, T, P, Tp, mean, rstd, part);
+                   const float* gamma, float* dgamma, float* dbeta, const Planes& dz, int dz_col0, float* dbias, float* part, cudaStream_t st,
+                   int tsplit) {
+    PPV_REQUIRE(C % 64 == 0 && tsplit >= 1 && tsplit <= 8, "bn_backward: C % 64 == 0 and 1 <= tsplit <= 8 required");
+    bn_bwd_reduce_kernel<<<dim3(C / 64, B, tsplit), TR_WARPS * 32, 0, st>>>(gl, a, a_col0, C, T, P, Tp, mean, rstd, part);
     TR_LAUNCH_OK("bn_bwd_reduce_kernel");
-    part_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(part, B, C, 2, dbeta, dgamma);
+    part_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(part, B * tsplit, C, 2, dbeta, dgamma);
     TR_LAUNCH_OK("part_finalize_kernel");
-    bn_bwd_apply_kernel<<<dim3(C / 64, B), TR_WARPS * 32, 0, st>>>(gl, a, a_col0, C, T, P, Tp, mean, rstd, gamma, dbeta, dgamma,
-                                                                  1.f / (float(B) * float(T)), dz, dz_col0, part);
+    bn_bwd_apply_kernel<<<dim3(C / 64, B, tsplit), TR_WARPS * 32, 0, st>>>(gl, a, a_col0, C, T, P, Tp, mean, rstd, gamma, dbeta, dgamma,
+                                                                          1.f / (float(B) * float(T)), dz, dz_col0, part);
     TR_LAUNCH_OK("bn_bwd_apply_kernel");
     if (dbias) {
-        part_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(part, B, C, 1, dbias, nullptr);
+        part_finalize_kernel<<<(C + 7) / 8, 256, 0, st>>>(part, B * tsplit, C, 1, dbias, nullptr);
         TR_LAUNCH_OK("part_finalize_kernel");
     }
     return PPV_OK;
@@ -672,9 +682,11 @@ int tr_grad_dot(const GradSrcList& gl, const Planes& y, int y_col0, int C, int B
     TR_LAUNCH_OK("grad_dot_kernel");
     return PPV_OK;
 }
-int tr_transpose(const Planes& in, int col0, int C, int64_t rows, const Planes& out, int shift, cudaStream_t st) {
-    PPV_REQUIRE(out.ld >= rows && out.rows >= C, "transpose: output too small");
-    transpose_planes_kernel<<<dim3(unsigned((out.ld + 31) / 32), (C + 31) / 32), 256, 0, st>>>(in, col0, C, rows, out, shift);
+int tr_transpose(const Planes& in, int col0, int C, int64_t rows, const Planes& out, int shift, cudaStream_t st, int ntaps, int shift_step,
+                 int64_t out_row_step) {
+    PPV_REQUIRE(out.ld >= rows && out.rows >= C + (ntaps - 1) * out_row_step, "transpose: output too small");
+    transpose_planes_kernel<<<dim3(unsigned((out.ld + 31) / 32), (C + 31) / 32, ntaps), 256, 0, st>>>(in, col0, C, rows, out, shift, shift_step,
+                                                                                                      out_row_step);
     TR_LAUNCH_OK("transpose_planes_kernel");
     return PPV_OK;
 }
