@@ -58,11 +58,11 @@ struct TStep {
     } kind;
     GemmParams gp;
     int BN = 0;
-    int a = 0, b = 0, c = 0;  // small integer arguments (layer ids, column offsets)
+    int a = 0, b = 0;  // small integer arguments (block index, split counts)
     GradSrcList gl;
     BnApplyArgs ap;
-    Planes p0, p1, p2;
-    int c0 = 0, c1 = 0, c2 = 0, C = 0;
+    Planes p0, p1;
+    int c0 = 0, c1 = 0, C = 0;
     float* f0 = nullptr;
     // WGRAD
     std::vector<GemmParams> wg;
@@ -104,13 +104,9 @@ struct Trainer {
     float *logits = nullptr, *se_s[3], *se_g1[3], *se_g2[3], *gstat = nullptr, *fold = nullptr, *pooled = nullptr, *pn = nullptr, *emb = nullptr,
           *cls_logits = nullptr, *loss = nullptr, *aspbn_mean = nullptr, *aspbn_rstd = nullptr;
     float *d_emb = nullptr, *dpn = nullptr, *dpooled = nullptr, *dgs = nullptr, *rs = nullptr, *rb = nullptr, *dg2 = nullptr, *dg1 = nullptr, *ds = nullptr,
-          *part = nullptr, *wpart = nullptr, *dummy = nullptr;
+          *part = nullptr, *wpart = nullptr;
     void* aam_ws = nullptr;
     size_t aam_ws_bytes = 0;
-    const float* feat = nullptr;
-    const int64_t* labels = nullptr;
-    float margin = 0.f, ascale = 32.f, label_smoothing = 0.f;
-    int easy_margin = 0;
 };
 
 // ------------------------------------------------------------------------------------------------ create: flat layout
@@ -324,7 +320,6 @@ void tr_carve(Trainer* t, TrCarve& k, int B, int T) {
     t->dg1 = k.f32(size_t(B) * t->se);
     t->ds = k.f32(size_t(B) * C);
     t->part = k.f32(size_t(3) * B * C3);
-    t->dummy = k.f32(2 * C3);
     // weight-gradient partials: max over layers of splits * Mpad * Ktot; splits <= num_sms
     size_t wmax = 0;
     auto wsize = [&](const TConv& c) {
@@ -367,7 +362,6 @@ static int tr_build_plan(Trainer* t, int B, int T, void* ws, size_t ws_bytes, cu
     const int M = int(t->R);
     float* const par = t->params;
     float* const grd = t->grads;
-    float* const sta = t->stats;
     int rc;
 
     auto push = [&](const TStep& s) { t->steps.push_back(s); };
@@ -689,7 +683,6 @@ static int tr_build_plan(Trainer* t, int B, int T, void* ws, size_t ws_bytes, cu
         rc = wgrad(t->l_conv0, c, t->dZ0, 0, {TStep::Tr{t->X0, 0, t->Fp, 0, 1}});
         if (rc) return rc;
     }
-    (void)sta;
     t->plan_ws = ws;
     t->plan_B = B;
     t->plan_T = T;
