@@ -79,6 +79,7 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_MAX_KSTEPS = 192;
 constexpr int GEMM_MAX_MAPS = 4;
+constexpr int GEMM_WS_STAGES = 4;  // ring slots in weight-stationary mode (the rest of the ring's shared memory holds W)
 
 struct KStep {
     int16_t map;      // which A tensor map
@@ -128,6 +129,7 @@ struct GemmParams {
     int num_ksteps;
     int bk;  // K elements per k-step (64 or 32)
     int l2_prefetch;  // producer prefetches the next tile's activation rows into L2
+    int ws;           // weight-stationary mode (set by gemm_build): W resident in shared memory, the ring carries activations only
     int lin_splits;   // > 0: weight-gradient mode (see gemm_build_wgrad): K runs over operand columns, split in lin_splits parts
     int lin_b_row0, lin_b_col0;
     int64_t lin_split_rows;

@@ -87,6 +87,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    // Weight-stationary mode (gp.ws, narrow convs with one n-tile and a small K): the whole weight matrix is loaded ONCE per CTA
+    // into the upper half of the ring's shared memory and the ring (4 slots) carries activation tiles only -- for the
+    // 32-channel 3x3 convs of the 2-D models the per-tile reload of the weights was a third of the L2 -> SM traffic.
+    const int nst = gp.ws ? GEMM_WS_STAGES : STAGES;
+    const uint32_t w_res = tiles_base + GEMM_WS_STAGES * Cfg::STAGE_BYTES;
+    const uint32_t w_full = bar_base + 8u * (2 * STAGES + 5);
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < GEMM_MAX_MAPS; ++i) prefetch_tmap(&gp.mapA[i]);
@@ -102,6 +108,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             mbar_init(tfull_bar(a), 1);
             mbar_init(tempty_bar(a), GEMM_EPI_THREADS);
         }
+        mbar_init(w_full, 1);
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -126,6 +133,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         // ===================== TMA producer =====================
         int stage = 0;
         uint32_t phase = 0;
+        if (gp.ws && lane == 0) {  // resident weights: every k-slice, once
+            mbar_arrive_expect_tx(w_full, nk * Cfg::NB * Cfg::B_BYTES);
+            for (int s = 0; s < nk; ++s)
+                for (int p = 0; p < Cfg::NB; ++p) tma_load_3d(w_res + (s * Cfg::NB + p) * Cfg::B_BYTES, &gp.mapB, w_full, s * BK, 0, p);
+        }
+        __syncwarp();
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int tmn = tile % mn_tiles, zsplit = tile / mn_tiles;
             const int m0 = (tmn / gp.n_tiles) * GEMM_BM;
@@ -148,8 +161,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                     const uint32_t sa = tiles_base + stage * Cfg::STAGE_BYTES;
                     const uint32_t sb = sa + Cfg::NA * Cfg::A_BYTES;
                     const uint32_t fb = full_bar(stage);
-                    mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
-                    if (gp.lin_splits > 0) {
+                    mbar_arrive_expect_tx(fb, gp.ws ? Cfg::NA * Cfg::A_BYTES : Cfg::STAGE_BYTES);
+                    if (gp.ws) {
+                        const KStep ks = gp.ksteps[s];
+#pragma unroll
+                        for (int p = 0; p < Cfg::NA; ++p) tma_load_3d(sa + p * Cfg::A_BYTES, &gp.mapA[ks.map], fb, ks.a_col, m0 + ks.row_off, p);
+                    } else if (gp.lin_splits > 0) {
                         const int kcol = (zsplit * nk + s) * BK;
 #pragma unroll
                         for (int p = 0; p < Cfg::NA; ++p) tma_load_3d(sa + p * Cfg::A_BYTES, &gp.mapA[0], fb, kcol, m0, p);
@@ -168,7 +185,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                     }
                 }
                 __syncwarp();
-                if (++stage == STAGES) {
+                if (++stage == nst) {
                     stage = 0;
                     phase ^= 1u;
                 }
@@ -181,6 +198,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         uint32_t phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
+        if (gp.ws) mbar_wait(w_full, 0);
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue drained this accumulator
             tc_fence_after();
@@ -190,7 +208,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t sa = tiles_base + stage * Cfg::STAGE_BYTES;
-                    const uint32_t sb = sa + Cfg::NA * Cfg::A_BYTES;
+                    const uint32_t sb = gp.ws ? w_res + s * Cfg::NB * Cfg::B_BYTES : sa + Cfg::NA * Cfg::A_BYTES;
                     const uint64_t a_hi = make_kmajor_desc<BK>(sa);
                     const uint64_t b_hi = make_kmajor_desc<BK>(sb);
                     // K advance inside the 128-byte swizzle atom: +32 B (16 bf16) per UMMA_K => +2 in desc.lo
@@ -209,7 +227,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                     if (s == nk - 1) umma_commit(tfull_bar(acc));   // accumulator complete
                 }
                 __syncwarp();
-                if (++stage == STAGES) {
+                if (++stage == nst) {
                     stage = 0;
                     phase ^= 1u;
                 }
@@ -325,6 +343,17 @@ int gemm_build(GemmParams* gp, const GemmSource* srcs, int nsrc, const Planes& W
     gp->m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
     gp->n_tiles = (N + BN - 1) / BN;
     gp->epi = epi;
+    {
+        // weight-stationary: one n-tile, all k-slices of W (both planes) fit next to a 4-slot ring, and enough tiles per CTA to pay
+        const size_t stage_bytes = size_t(2) * GEMM_BM * BK * 2 + size_t(2) * BN * BK * 2;
+        const size_t stages_full = std::min<size_t>(8, (232448 - 1024 - EPI_STAGING_BYTES - 256) / stage_bytes);
+        const size_t w_bytes = size_t(ks) * 2 * BN * BK * 2;
+        const char* wsenv = getenv("PPV_GEMM_WS");
+        gp->ws = (gp->n_tiles == 1 && stages_full > GEMM_WS_STAGES && w_bytes <= (stages_full - GEMM_WS_STAGES) * stage_bytes && gp->m_tiles >= 296 &&
+                  !(wsenv && wsenv[0] == '0'))
+                     ? 1
+                     : 0;
+    }
     {
         const char* ns = getenv("PPV_GEMM_NOSTORE");
         gp->epi.debug_nostore = (ns && ns[0] == '1') ? 1 : 0;
