@@ -1,4 +1,4 @@
-"""Debug aid: per-parameter gradient error of the CUDA training step vs the fp64 autograd oracle (prints every tensor)."""
+"""Debug aid (test infrastructure -- it imports oracle/, so it lives under tests/): per-parameter gradient error of the CUDA training step vs the fp64 autograd oracle (prints every tensor)."""
 import os
 import sys
 

@@ -5,7 +5,7 @@ Tolerances.  Activations and activation gradients are stored as split-bf16 plane
 contraction is the 3-pass bf16 one: the forward agrees with fp64 to ~3e-5, the gradients of the head to ~5e-5.  Each train-mode
 BatchNorm backward projects out the mean and the x-hat component of its incoming gradient, which amplifies the relative error of
 what is left, so the error grows towards the input: ~2e-4 below the pooling layer, ~5e-3 at the first conv (measured,
-tools/train_grad_check.py).  The reference trains with fp16 autocast (trainer.py:209) at a far looser precision.  Asserted here:
+tests/grad_check_tool.py).  The reference trains with fp16 autocast (trainer.py:209) at a far looser precision.  Asserted here:
 every parameter gradient within 5e-2 relative (L2, per tensor; the worst are 64-element bias gradients, sums that cancel) with
 cosine > 0.999 to the fp64 gradient, and the head within 5e-4."""
 import numpy as np
