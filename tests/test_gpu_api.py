@@ -143,6 +143,32 @@ def test_trainer_extract_features_and_evaluate(cuda, wavs, cfg, W64, tmp_path):
     assert abs(min_dcf - float(compute_dcf(fnr, fpr))) < 1e-6
 
 
+@pytest.mark.parametrize("model_name", ["CAMPPlus", "ERes2Net", "ResNetSE"])
+def test_predictor_with_the_other_backbones(cuda, wavs, cfg, model_name):
+    """PPVectorPredictor (predict.py:218-283) is model-agnostic in the reference: the same surface must drive every backbone."""
+    import copy
+    import importlib
+    paths, g = wavs
+    cfg = copy.deepcopy(cfg)
+    cfg["model_conf"]["model"] = model_name
+    cfg["model_conf"]["model_args"] = {"embd_dim": 192}
+    om = importlib.import_module({"CAMPPlus": "oracle.campplus", "ERes2Net": "oracle.eres2net", "ResNetSE": "oracle.resnet_se"}[model_name])
+    make = {"CAMPPlus": "make_campplus_weights", "ERes2Net": "make_eres2net_weights", "ResNetSE": "make_resnet_se_weights"}[model_name]
+    fwd = {"CAMPPlus": "campplus_forward", "ERes2Net": "eres2net_forward", "ResNetSE": "resnet_se_forward"}[model_name]
+    Wm = getattr(om, make)(seed=1000, dtype=torch.float64)
+    p = PPVectorPredictor(configs=cfg, state_dict={k: v.float().numpy() for k, v in Wm.items()})
+    emb = p.predict(paths["a_2"])
+    x = ofb.db_normalize(g["a_2_pcm"].astype(np.float32) / 32768.0, -20.0)
+    feat = torch.from_numpy(ofb.audio_featurizer_fbank(x, None, dtype=np.float64, n_mels=80))
+    ref = getattr(om, fwd)(feat, Wm)[0].numpy()
+    cos = float((emb * ref).sum() / np.linalg.norm(emb) / np.linalg.norm(ref))
+    assert emb.shape == (192,) and 1 - cos < 1e-6, cos
+    s = p.contrast(paths["a_2"], paths["b_2"])
+    e2 = getattr(om, fwd)(torch.from_numpy(ofb.audio_featurizer_fbank(ofb.db_normalize(g["b_2_pcm"].astype(np.float32) / 32768.0, -20.0), None,
+                                                                      dtype=np.float64, n_mels=80)), Wm)[0].numpy()
+    assert abs(s - float((ref * e2).sum() / np.linalg.norm(ref) / np.linalg.norm(e2))) < 1e-4
+
+
 def test_trainer_train_runs_the_cuda_step(cuda, wavs, cfg, tmp_path):
     """PPVectorTrainer.train (trainer.py:281-365): list file -> features -> SpecAugment -> CUDA training step -> Adam with the
     reference's LR / margin schedules -> checkpoint with the reference's key names -> evaluate on it."""

@@ -88,6 +88,11 @@ class NativeBackbone(nn.Module):
                                                       ws.numel(), _lib.current_stream()), 'ppv_model_forward')
         return emb
 
+    def forward_wav(self, featurizer, waveforms, input_lens_ratio=None):
+        """waveforms [N, samples] -> [N, embd_dim]: featurise, then embed (two library calls).  EcapaTdnn overrides this with the
+        fused ``ppv_model_forward_wav`` path when the front end is Fbank."""
+        return self(featurizer(waveforms, input_lens_ratio))
+
     def _read_tap(self, name, shape):
         out = torch.empty(shape, dtype=torch.float32, device=self._ws.device)
         _lib.check(_lib.load().ppv_model_read_tap(self._get_handle(), name.encode(), _lib.ptr(out), out.numel(),

@@ -209,6 +209,8 @@ class EcapaTdnn(nn.Module):
     def forward_wav(self, featurizer, waveforms, input_lens_ratio=None):
         """Fused waveform -> embedding path (``ppv_model_forward_wav``): equals
         ``self(featurizer(waveforms, input_lens_ratio))`` without materialising the [B,T,F] features."""
+        if getattr(featurizer, '_feature_method', 'Fbank') != 'Fbank':  # the fused path is Fbank -> ECAPA; other front ends: two calls
+            return super().forward_wav(featurizer, waveforms, input_lens_ratio)
         _lib.require_cuda(waveforms, 'waveforms')
         if waveforms.dim() == 1:
             waveforms = waveforms.unsqueeze(0)
