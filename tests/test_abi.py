@@ -70,3 +70,25 @@ def test_product_never_imports_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(d, fn), errors="replace").read()
                 assert "import oracle" not in txt and "from oracle" not in txt, os.path.join(d, fn)
+
+
+def test_every_shipped_config_builds_its_backbone():
+    """configs/*.yml keep the reference's schema; build_model (models/__init__.py:15-21) must construct each backbone from it
+    (parameter holders only: no GPU, no library call)."""
+    import glob
+    import os
+
+    import yaml
+
+    from ppvector.models import build_model
+    from ppvector.utils.utils import dict_to_object
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    seen = {}
+    for path in sorted(glob.glob(os.path.join(root, "configs", "*.yml"))):
+        cfg = dict_to_object(yaml.load(open(path), Loader=yaml.FullLoader))
+        for key in ("dataset_conf", "preprocess_conf", "model_conf", "loss_conf", "optimizer_conf", "train_conf"):
+            assert key in cfg, (path, key)
+        m = build_model(input_size=80, configs=cfg)
+        seen[cfg.model_conf.model] = sum(p.numel() for p in m.parameters())
+    assert set(seen) == {"EcapaTdnn", "ResNetSE", "ERes2Net", "CAMPPlus"}
+    assert seen["EcapaTdnn"] == 6194048 and seen["ERes2Net"] == 6620128 and seen["CAMPPlus"] == 6859232
