@@ -31,6 +31,13 @@ extern "C" {
 #define PPV_PREC_BF16X3 0 /* split-bf16, 3 MMAs per product: fp32-grade (parity mode, default) */
 #define PPV_PREC_BF16 1   /* single bf16 MMA: fast mode, ~1e-2 relative on embeddings */
 
+/* EcapaTdnn(pooling_type=...): ASP = attentive statistics (pooling.py:69-125), SAP = self-attentive (:50-66),
+ * TAP = temporal average (:8-25), TSP = temporal mean | unbiased variance (:28-47). */
+#define PPV_POOL_ASP 0
+#define PPV_POOL_SAP 1
+#define PPV_POOL_TAP 2
+#define PPV_POOL_TSP 3
+
 typedef struct ppv_fbank ppv_fbank_t;
 typedef struct ppv_model ppv_model_t;
 
@@ -131,6 +138,7 @@ typedef struct {
     int res2net_scale;      /* 8 */
     int se_channels;        /* 128 */
     int precision;          /* PPV_PREC_* */
+    int pooling;            /* PPV_POOL_*: ecapa_tdnn.py:212-241 pooling_type */
 } ppv_ecapa_cfg;
 
 void ppv_ecapa_default_cfg(ppv_ecapa_cfg* cfg);

@@ -132,7 +132,8 @@ def attentive_stats_pool(x, W, prefix="asp", lengths=None, global_context=True, 
 
 
 def ecapa_forward(feats, W: Dict[str, torch.Tensor], lengths: Optional[torch.Tensor] = None,
-                  dilations=(1, 2, 3, 4, 1), res2net_scale=8, taps: Optional[dict] = None, bn=batchnorm_eval, layer_taps=False):
+                  dilations=(1, 2, 3, 4, 1), res2net_scale=8, taps: Optional[dict] = None, bn=batchnorm_eval, layer_taps=False,
+                  pooling_type="ASP"):
     """ecapa_tdnn.py:245-276.  feats [B,T,F] -> embedding [B,embd_dim].
 
     ``taps`` (optional dict) is filled with intermediate activations for per-layer
@@ -154,10 +155,26 @@ def ecapa_forward(feats, W: Dict[str, torch.Tensor], lengths: Optional[torch.Ten
     x = tdnn_block(x, W, "mfa", dilations[-1], bn)
     if taps is not None:
         taps["mfa"] = x
-    x = attentive_stats_pool(x, W, "asp", lengths, bn=bn)
-    if taps is not None:
-        taps["asp"] = x
-    x = bn(x, W, "asp_bn.norm")
+    if pooling_type == "ASP":
+        x = attentive_stats_pool(x, W, "asp", lengths, bn=bn)
+        if taps is not None:
+            taps["asp"] = x
+        x = bn(x, W, "asp_bn.norm")
+    else:
+        # ecapa_tdnn.py:221-241 with pooling.py:8-66; these heads use paddle.nn.BatchNorm1D directly (keys asp_bn.weight, ...)
+        if pooling_type == "SAP":
+            a = torch.tanh(F.conv1d(x, W["asp.linear1.weight"], W["asp.linear1.bias"]))
+            a = F.softmax(F.conv1d(a, W["asp.linear2.weight"], W["asp.linear2.bias"]), dim=2)
+            x = (a * x).sum(dim=2)
+        elif pooling_type == "TAP":
+            x = x.mean(dim=2)
+        elif pooling_type == "TSP":
+            x = torch.cat((x.mean(dim=2), x.var(dim=2, unbiased=True)), dim=1)
+        else:
+            raise Exception(f"unknown pooling_type {pooling_type}")
+        if taps is not None:
+            taps["asp"] = x
+        x = bn(x, W, "asp_bn")
     x = F.conv1d(x.unsqueeze(2), W["fc.conv.weight"], W["fc.conv.bias"]).squeeze(-1)
     return x
 
@@ -167,7 +184,7 @@ def ecapa_forward(feats, W: Dict[str, torch.Tensor], lengths: Optional[torch.Ten
 # ----------------------------------------------------------------------------------------------
 def ecapa_param_shapes(input_size=80, embd_dim=192, channels=(512, 512, 512, 512, 1536),
                        kernel_sizes=(5, 3, 3, 3, 1), attention_channels=128, res2net_scale=8,
-                       se_channels=128):
+                       se_channels=128, pooling_type="ASP"):
     """Name -> shape for every tensor in the reference EcapaTdnn state_dict (ecapa_tdnn.py:145-243)."""
     S = {}
 
@@ -197,10 +214,18 @@ def ecapa_param_shapes(input_size=80, embd_dim=192, channels=(512, 512, 512, 512
             conv(p + ".shortcut.conv", cin, cout, 1)
     C = channels[-1]
     tdnn("mfa", C, C, kernel_sizes[-1])
-    tdnn("asp.tdnn", 3 * C, attention_channels, 1)
-    conv("asp.conv.conv", attention_channels, C, 1)
-    bn("asp_bn.norm", 2 * C)
-    conv("fc.conv", 2 * C, embd_dim, 1)
+    if pooling_type == "ASP":
+        tdnn("asp.tdnn", 3 * C, attention_channels, 1)
+        conv("asp.conv.conv", attention_channels, C, 1)
+        bn("asp_bn.norm", 2 * C)
+        conv("fc.conv", 2 * C, embd_dim, 1)
+        return S
+    pooled = 2 * C if pooling_type == "TSP" else C
+    if pooling_type == "SAP":
+        conv("asp.linear1", C, 128, 1)
+        conv("asp.linear2", 128, C, 1)
+    bn("asp_bn", pooled)
+    conv("fc.conv", pooled, embd_dim, 1)
     return S
 
 
@@ -212,9 +237,9 @@ def make_ecapa_weights(seed=1000, dtype=torch.float32, **shape_args) -> Dict[str
     g = torch.Generator().manual_seed(seed)
     W = {}
     for name, shape in ecapa_param_shapes(**shape_args).items():
-        if name.endswith("_variance") or (name.endswith("norm.weight")):
+        if name.endswith("_variance") or name.endswith("norm.weight") or name == "asp_bn.weight":
             t = torch.rand(shape, generator=g, dtype=torch.float64) + 0.5
-        elif name.endswith("_mean") or name.endswith("norm.bias"):
+        elif name.endswith("_mean") or name.endswith("norm.bias") or name == "asp_bn.bias":
             t = torch.randn(shape, generator=g, dtype=torch.float64) * 0.1
         elif name.endswith(".weight"):
             fan_in = shape[1] * shape[2]

@@ -131,3 +131,27 @@ def test_full_size_properties(cuda, model):
     for b in (0, 100, 255):
         single = model(f[b:b + 1])
         assert torch.equal(single, emb[b:b + 1])
+
+
+@pytest.mark.parametrize("pooling_type", ["SAP", "TAP", "TSP"])
+@pytest.mark.parametrize("T", [98, 298])
+def test_other_pooling_types(cuda, pooling_type, T):
+    """EcapaTdnn(pooling_type=...) of the reference (ecapa_tdnn.py:212-243, pooling.py:8-66): self-attentive, average and
+    mean | unbiased-variance pooling, each followed by paddle.nn.BatchNorm1D and the fc conv."""
+    from oracle import ecapa as oe_
+    from ppvector.models.ecapa_tdnn import EcapaTdnn as Model
+    W = oe_.make_ecapa_weights(seed=1000, dtype=torch.float64, pooling_type=pooling_type)
+    m = Model(input_size=80, pooling_type=pooling_type).eval()
+    m.load_state_dict({k: v.float() for k, v in W.items()}, strict=True)
+    m.to(cuda)
+    gi = torch.Generator().manual_seed(77 + T)
+    f = torch.randn(3, T, 80, generator=gi, dtype=torch.float64)
+    f = f - f.mean(1, keepdim=True)
+    ref = oe_.ecapa_forward(f, W, pooling_type=pooling_type)
+    emb = m(f.float().to(cuda)).double().cpu()
+    rel = (emb - ref).norm(dim=1) / ref.norm(dim=1)
+    assert rel.max() < 1e-4, (pooling_type, rel)
+    cos = torch.nn.functional.cosine_similarity(emb, ref)
+    assert (1 - cos).max() < 1e-8
+    with pytest.raises(Exception):
+        Model(input_size=80, pooling_type="XYZ")

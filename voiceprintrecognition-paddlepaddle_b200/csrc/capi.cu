@@ -139,6 +139,7 @@ void ppv_ecapa_default_cfg(ppv_ecapa_cfg* c) {
     c->res2net_scale = 8;
     c->se_channels = 128;
     c->precision = PPV_PREC_BF16X3;
+    c->pooling = PPV_POOL_ASP;
 }
 
 void ppv_eres2net_default_cfg(ppv_eres2net_cfg* c) {

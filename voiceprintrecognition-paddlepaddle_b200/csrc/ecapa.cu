@@ -46,7 +46,7 @@ struct KSpec {  // one K group: `ncols` columns of a source at a row offset <- w
 enum Buf { B_FEAT, B_X0, B_H, B_Y, B_Z, B_CAT, B_MFA, B_ATT, B_GSTAT, B_POOL, B_SEM, B_SEH, B_COUNT };
 
 struct Step {
-    enum Kind { GEMM, RES2, RES2CHAIN, SE_SQUEEZE, SE_SCALE, ASP_GLOBAL, ASP_FUSED } kind;
+    enum Kind { GEMM, RES2, RES2CHAIN, SE_SQUEEZE, SE_SCALE, ASP_GLOBAL, ASP_FUSED, POOL_STATS } kind;
     GemmParams gp;
     AspFusedParams ap;
     Res2Params rp;
@@ -103,6 +103,7 @@ int ecapa_create(const ppv_ecapa_cfg* cfg, EcapaModel** out) {
         return fail(PPV_EUNSUPPORTED, "ecapa: kernel sizes must be [odd,3,3,3,1]");
     if (cfg->attention_channels % 64 || cfg->embd_dim % 32 || cfg->se_channels <= 0 || cfg->se_channels % 64)
         return fail(PPV_EUNSUPPORTED, "ecapa: attention_channels % 64, se_channels % 64, embd_dim % 32 required");
+    if (cfg->pooling < PPV_POOL_ASP || cfg->pooling > PPV_POOL_TSP) return fail(PPV_EUNSUPPORTED, "ecapa: pooling must be PPV_POOL_ASP / SAP / TAP / TSP");
     EcapaModel* m = new EcapaModel();
     m->cfg = *cfg;
     m->precision = cfg->precision;
@@ -300,6 +301,32 @@ int ecapa_finalize(EcapaModel* m) {
         ok = ok && conv_layer(&m->se2[b - 1], p + ".se_block.conv2.conv", C, S, 1, {{B_SEH, 0, S, 0, 0, S, 0}}, "", true);
     }
     ok = ok && conv_layer(&m->mfa, "mfa.conv.conv", C3, C3, 1, {{B_CAT, 0, C3, 0, 0, C3, 0}}, "mfa.norm.norm", true);
+    const int pooling = m->cfg.pooling;
+    // BatchNorm(eval) + Linear after a parameter-free or self-attentive pooling: fc(bn(p)) = (W diag(s)) p + (W t + b), folded here
+    auto folded_fc = [&](int Kp) -> bool {
+        const HostW* w = f.get("fc.conv.weight", {E, Kp, 1});
+        const HostW* b = f.get("fc.conv.bias", {E});
+        std::vector<float> sc, sh;
+        if (!w || !b || !f.bn_affine("asp_bn", Kp, &sc, &sh)) return false;  // paddle.nn.BatchNorm1D: keys asp_bn.weight / ._mean ...
+        HostW wf;
+        wf.shape = {E, Kp, 1};
+        wf.v.resize(size_t(E) * Kp);
+        std::vector<float> bf(E);
+        for (int n = 0; n < E; ++n) {
+            double acc = b->v[n];
+            for (int k = 0; k < Kp; ++k) {
+                wf.v[size_t(n) * Kp + k] = w->v[size_t(n) * Kp + k] * sc[k];
+                acc += double(w->v[size_t(n) * Kp + k]) * sh[k];
+            }
+            bf[n] = float(acc);
+        }
+        size_t off;
+        f.put_conv(&m->fc, &wf, E, Kp, 1, {{B_POOL, 0, Kp, 0, 0, Kp, 0}}, &off);
+        patch(&m->fc.W.base, off);
+        put_vec(&m->fc.bias, bf);
+        return true;
+    };
+    if (pooling == PPV_POOL_ASP) {
     // ASP attention TDNN: weight [A, 3*C3, 1] split into the x part (cols 0..C3) and the [mean;std] part
     ok = ok && conv_layer(&m->att1, "asp.tdnn.conv.conv", A, 3 * C3, 1, {{B_MFA, 0, C3, 0, 0, C3, 0}}, "asp.tdnn.norm.norm", true);
     if (ok) {
@@ -317,6 +344,23 @@ int ecapa_finalize(EcapaModel* m) {
             put_vec(&m->aspbn_scale, sc);
             put_vec(&m->aspbn_shift, sh);
         }
+    }
+    } else if (pooling == PPV_POOL_SAP) {
+        // SelfAttentivePooling (pooling.py:50-66): alpha = softmax_t(linear2(tanh(linear1(x)))); mean = sum alpha x.  The fused ASP
+        // kernel computes exactly this weighted mean (its std half is ignored); linear2's bias cancels in the softmax.
+        if (A != 128) {
+            f.err = "SAP pooling uses a 128-channel bottleneck (ecapa_tdnn.py:222): attention_channels must be 128";
+            ok = false;
+        }
+        ok = ok && conv_layer(&m->att1, "asp.linear1", A, C3, 1, {{B_MFA, 0, C3, 0, 0, C3, 0}}, "", true);
+        ok = ok && conv_layer(&m->att2, "asp.linear2", C3, A, 1, {{B_ATT, 0, A, 0, 0, A, 0}}, "", true);
+        ok = ok && folded_fc(C3);
+        if (ok) {
+            put_vec(&m->aspbn_scale, std::vector<float>(2 * C3, 1.f));
+            put_vec(&m->aspbn_shift, std::vector<float>(2 * C3, 0.f));
+        }
+    } else {
+        ok = ok && folded_fc(pooling == PPV_POOL_TAP ? C3 : 2 * C3);
     }
     if (!ok) return fail(PPV_EINVAL, "ecapa_finalize: " + f.err);
     PPV_CUDA_OK(cudaMalloc(&m->arena, f.host.size()));
@@ -527,12 +571,17 @@ static int build_plan(EcapaModel* m, int B, int T, void* ws, size_t ws_bytes, cu
     }
     rc = add_gemm(m->mfa, {{B_CAT, 0, C3, 0, 0, C3, 0}}, nullptr, 0, int(R), planes_out(m->bufs[B_MFA], 0, false));
     if (rc) return rc;
-    {
+    const int pooling = m->cfg.pooling;
+    if (pooling == PPV_POOL_TAP || pooling == PPV_POOL_TSP) {
+        Step s;  // mean (TAP) or mean | unbiased variance (TSP) over time, straight into the fc operand
+        s.kind = Step::POOL_STATS;
+        m->steps.push_back(s);
+    } else {
         Step s;
         s.kind = Step::ASP_GLOBAL;
         m->steps.push_back(s);
     }
-    {  // fold: [B, 2*C3] . W[:, C3:3*C3]^T -> per-utterance bias [B, att]  (no conv bias here)
+    if (pooling == PPV_POOL_ASP) {  // fold: [B, 2*C3] . W[:, C3:3*C3]^T -> per-utterance bias [B, att]  (no conv bias here)
         Epilogue ep;
         ep.out_mode = OUT_F32;
         ep.out = m->fold_out;
@@ -542,27 +591,34 @@ static int build_plan(EcapaModel* m, int B, int T, void* ws, size_t ws_bytes, cu
         rc = add_gemm(cw, {{B_GSTAT, 0, 2 * C3, 0, 0, 0, 0}}, nullptr, 0, B, ep);
         if (rc) return rc;
     }
-    {  // attention TDNN (K = C3) + per-utterance bias -> ReLU -> BN -> tanh
-        Epilogue ep = planes_out(m->bufs[B_ATT], 0, false);
-        ep.rowgrp_bias = m->fold_out;
-        ep.tanh_ = 1;
-        rc = add_gemm(m->att1, {{B_MFA, 0, C3, 0, 0, 0, 0}}, nullptr, 0, int(R), ep);
-        if (rc) return rc;
+    if (pooling == PPV_POOL_ASP || pooling == PPV_POOL_SAP) {
+        {  // ASP: attention TDNN (K = C3) + per-utterance bias -> ReLU -> BN -> tanh;  SAP: tanh(linear1(x))
+            Epilogue ep = planes_out(m->bufs[B_ATT], 0, false);
+            if (pooling == PPV_POOL_ASP) {
+                ep.rowgrp_bias = m->fold_out;
+            } else {
+                ep.relu = 0;
+            }
+            ep.tanh_ = 1;
+            rc = add_gemm(m->att1, {{B_MFA, 0, C3, 0, 0, 0, 0}}, nullptr, 0, int(R), ep);
+            if (rc) return rc;
+        }
+        {  // attention logits (transposed GEMM) + softmax over time + weighted mean / std + asp_bn, fused
+            Step s;
+            s.kind = Step::ASP_FUSED;
+            rc = asp_fused_build(&s.ap, m->att2.W, m->bufs[B_ATT], m->bufs[B_MFA], m->bufs[B_GSTAT], m->aspbn_scale, m->aspbn_shift,
+                                 m->bufs[B_POOL], m->pooled_raw, B, T, P, Tp, C3, m->att, 1e-12f);
+            if (rc) return rc;
+            m->steps.push_back(s);
+        }
     }
-    {  // attention logits (transposed GEMM) + softmax over time + weighted mean / std + asp_bn, fused
-        Step s;
-        s.kind = Step::ASP_FUSED;
-        rc = asp_fused_build(&s.ap, m->att2.W, m->bufs[B_ATT], m->bufs[B_MFA], m->bufs[B_GSTAT], m->aspbn_scale, m->aspbn_shift,
-                             m->bufs[B_POOL], m->pooled_raw, B, T, P, Tp, C3, m->att, 1e-12f);
-        if (rc) return rc;
-        m->steps.push_back(s);
-    }
-    {  // fc: [B, 2*C3] -> [B, embd]
+    {  // fc: pooled [B, Kp] -> [B, embd]
         Epilogue ep;
         ep.out_mode = OUT_F32;
         ep.out = m->emb_out;
         ep.out_ld = m->cfg.embd_dim;
-        rc = add_gemm(m->fc, {{B_POOL, 0, 2 * C3, 0, 0, 0, 0}}, nullptr, 0, B, ep);
+        const int Kp = (pooling == PPV_POOL_ASP || pooling == PPV_POOL_TSP) ? 2 * C3 : C3;
+        rc = add_gemm(m->fc, {{B_POOL, 0, Kp, 0, 0, 0, 0}}, nullptr, 0, B, ep);
         if (rc) return rc;
     }
     m->plan_ws = ws;
@@ -649,6 +705,9 @@ int ecapa_forward(EcapaModel* m, const float* feat, Fbank* fb, const float* wav,
                 break;
             case Step::ASP_FUSED:
                 rc = asp_fused_launch(s.ap, m->precision, m->num_sms, st);
+                break;
+            case Step::POOL_STATS:
+                rc = launch_colstats(m->bufs[B_MFA], 0, C3, B, T, P, Tp, m->cfg.pooling == PPV_POOL_TAP ? 0 : 3, 0.f, nullptr, m->bufs[B_POOL], st);
                 break;
         }
         prof_mark(0, false);

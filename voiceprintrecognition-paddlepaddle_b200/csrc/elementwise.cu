@@ -85,6 +85,7 @@ __device__ __forceinline__ float2 block_colsum(float2 v, float2 (*s_part)[32], i
 // mode 0: mean -> out_f32[b, C] and/or planes [B, C]                                  (SE squeeze)
 // mode 1: mean and std = sqrt(clip(var, eps)) -> planes [B, 2C] (mean | std)             (ASP global context)
 // mode 2: mean and std = sqrt(var_unbiased + eps) -> planes [B, 2C]                       (TSTP, pooling.py:138-146)
+// mode 3: mean and var_unbiased -> planes [B, 2C]                                          (TSP, pooling.py:42-45)
 // Single pass with a per-channel shift K = x[first frame]: sum(x-K), sum((x-K)^2); var = (Q - S^2/T)/T.
 // Each lane owns 8 channels (one 16-byte load per plane), 4 frames per warp, 32 frames per block iteration.
 __global__ void __launch_bounds__(STAT_WARPS * 32)
@@ -166,7 +167,10 @@ __global__ void __launch_bounds__(STAT_WARPS * 32)
         } else {
             // mode 1: ASP global std = sqrt(clip(var_biased, eps)); mode 2: TSTP std = sqrt(var_unbiased + eps)
             const float ssq = Q - S * S * inv;
-            const float sd = (mode == 2) ? sqrtf(fmaxf(ssq, 0.f) / float(T > 1 ? T - 1 : 1) + eps) : sqrtf(fmaxf(ssq * inv, eps));
+            // mode 3: unbiased VARIANCE, no square root (TemporalStatisticsPooling, pooling.py:44)
+            const float sd = (mode == 2)   ? sqrtf(fmaxf(ssq, 0.f) / float(T > 1 ? T - 1 : 1) + eps)
+                             : (mode == 3) ? fmaxf(ssq, 0.f) / float(T > 1 ? T - 1 : 1)
+                                           : sqrtf(fmaxf(ssq * inv, eps));
             __nv_bfloat16 h, l;
             split_bf16(mean, h, l);
             out_pl.hi()[int64_t(b) * out_pl.ld + cc] = h;

@@ -12,6 +12,7 @@ LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "lib", "libppv_b200.so"))
 PPV_PREC_BF16X3 = 0
 PPV_PREC_BF16 = 1
 PPV_MODEL_ECAPA_TDNN = 1
+PPV_POOL_ASP, PPV_POOL_SAP, PPV_POOL_TAP, PPV_POOL_TSP = 0, 1, 2, 3
 
 
 class PPVError(RuntimeError):
@@ -27,7 +28,7 @@ class FbankCfg(C.Structure):
 class EcapaCfg(C.Structure):
     _fields_ = [("input_size", C.c_int), ("embd_dim", C.c_int), ("channels", C.c_int * 5),
                 ("kernel_sizes", C.c_int * 5), ("dilations", C.c_int * 5), ("attention_channels", C.c_int),
-                ("res2net_scale", C.c_int), ("se_channels", C.c_int), ("precision", C.c_int)]
+                ("res2net_scale", C.c_int), ("se_channels", C.c_int), ("precision", C.c_int), ("pooling", C.c_int)]
 
 
 class ResNetSECfg(C.Structure):

@@ -13,6 +13,7 @@ import torch
 from torch import nn
 
 from ppvector import _lib
+from ppvector.models._native import BNParams, ConvParams, Empty
 
 __all__ = ['EcapaTdnn']
 
@@ -108,15 +109,27 @@ class AttentiveStatisticsPooling(nn.Module):
         self.conv = Conv1d(attention_channels, channels, 1)
 
 
+class SelfAttentivePooling(nn.Module):
+    """reference: ppvector/models/pooling.py:50-58 (two plain paddle.nn.Conv1D: keys linear1.weight [128, C, 1], ...)"""
+
+    def __init__(self, in_dim, bottleneck_dim=128):
+        super().__init__()
+        self.linear1 = ConvParams(in_dim, bottleneck_dim, 1)
+        self.linear2 = ConvParams(bottleneck_dim, in_dim, 1)
+
+
 class EcapaTdnn(nn.Module):
+    _POOLING = {"ASP": _lib.PPV_POOL_ASP, "SAP": _lib.PPV_POOL_SAP, "TAP": _lib.PPV_POOL_TAP, "TSP": _lib.PPV_POOL_TSP}
+
     def __init__(self, input_size, embd_dim=192, pooling_type="ASP", activation=None,
                  channels=[512, 512, 512, 512, 1536], kernel_sizes=[5, 3, 3, 3, 1], dilations=[1, 2, 3, 4, 1],
                  attention_channels=128, res2net_scale=8, se_channels=128, global_context=True,
                  precision='bf16x3'):
         super().__init__()
         assert len(channels) == len(kernel_sizes) == len(dilations) == 5
-        if pooling_type != "ASP":
-            raise NotImplementedError(f'pooling_type {pooling_type} is not implemented on B200 (ASP only)')
+        if pooling_type not in self._POOLING:
+            raise Exception(f'没有{pooling_type}池化层！')  # ecapa_tdnn.py:242-243
+        self.pooling_type = pooling_type
         self.input_size, self.channels, self.embd_dim = input_size, list(channels), embd_dim
         self.kernel_sizes, self.dilations = list(kernel_sizes), list(dilations)
         self.attention_channels, self.res2net_scale, self.se_channels = attention_channels, res2net_scale, se_channels
@@ -126,9 +139,23 @@ class EcapaTdnn(nn.Module):
             self.blocks.append(SERes2NetBlock(channels[i - 1], channels[i], res2net_scale, se_channels,
                                               kernel_sizes[i], dilations[i]))
         self.mfa = TDNNBlock(channels[-1], channels[-1], kernel_sizes[-1], dilations[-1])
-        self.asp = AttentiveStatisticsPooling(channels[-1], attention_channels, global_context)
-        self.asp_bn = BatchNorm1d(channels[-1] * 2)
-        self.fc = Conv1d(channels[-1] * 2, embd_dim, 1)
+        cat_channels = channels[-1]
+        if pooling_type == "ASP":  # ecapa_tdnn.py:212-220
+            self.asp = AttentiveStatisticsPooling(cat_channels, attention_channels, global_context)
+            self.asp_bn = BatchNorm1d(cat_channels * 2)
+            self.fc = Conv1d(cat_channels * 2, embd_dim, 1)
+        elif pooling_type == "SAP":  # :221-227: SelfAttentivePooling(cat_channels, 128), paddle.nn.BatchNorm1D (keys asp_bn.weight ...)
+            self.asp = SelfAttentivePooling(cat_channels, 128)
+            self.asp_bn = BNParams(cat_channels)
+            self.fc = Conv1d(cat_channels, embd_dim, 1)
+        elif pooling_type == "TAP":  # :228-234
+            self.asp = Empty()
+            self.asp_bn = BNParams(cat_channels)
+            self.fc = Conv1d(cat_channels, embd_dim, 1)
+        else:  # TSP, :235-241
+            self.asp = Empty()
+            self.asp_bn = BNParams(cat_channels * 2)
+            self.fc = Conv1d(cat_channels * 2, embd_dim, 1)
         self.precision = precision
         self._handle = None
         self._ws = None
@@ -159,6 +186,7 @@ class EcapaTdnn(nn.Module):
             cfg.channels[i], cfg.kernel_sizes[i], cfg.dilations[i] = self.channels[i], self.kernel_sizes[i], self.dilations[i]
         cfg.attention_channels, cfg.res2net_scale, cfg.se_channels = self.attention_channels, self.res2net_scale, self.se_channels
         cfg.precision = self._prec_code()
+        cfg.pooling = self._POOLING[self.pooling_type]
         h = C.c_void_p()
         _lib.check(lib.ppv_model_create(_lib.PPV_MODEL_ECAPA_TDNN, C.byref(cfg), C.byref(h)), 'ppv_model_create')
         for name, t in self.state_dict().items():
@@ -210,7 +238,7 @@ class EcapaTdnn(nn.Module):
         """Fused waveform -> embedding path (``ppv_model_forward_wav``): equals
         ``self(featurizer(waveforms, input_lens_ratio))`` without materialising the [B,T,F] features."""
         if getattr(featurizer, '_feature_method', 'Fbank') != 'Fbank':  # the fused path is Fbank -> ECAPA; other front ends: two calls
-            return super().forward_wav(featurizer, waveforms, input_lens_ratio)
+            return self(featurizer(waveforms, input_lens_ratio))
         _lib.require_cuda(waveforms, 'waveforms')
         if waveforms.dim() == 1:
             waveforms = waveforms.unsqueeze(0)
