@@ -1,19 +1,21 @@
-"""build_loss -- reference: ppvector/loss/__init__.py:16-22."""
-import importlib
-
+"""Loss factory keyed by ``loss_conf.loss`` (the reference's ppvector/loss/__init__.py:16-22 resolves the name by reflection over
+seven losses; this build implements AAMLoss, the one every shipped config uses, and says so for the others)."""
 from loguru import logger
 
 from .aamloss import AAMLoss
 
-__all__ = ['build_loss']
+__all__ = ['build_loss', 'AAMLoss']
+
+_IMPLEMENTED = {'AAMLoss': AAMLoss}
+_REFERENCE_ONLY = ('AMLoss', 'ARMLoss', 'CELoss', 'SphereFace2', 'SubCenterLoss', 'TripletAngularMarginLoss')
 
 
 def build_loss(configs):
-    use_loss = configs.loss_conf.get('loss', 'AAMLoss')
-    loss_args = configs.loss_conf.get('loss_args', {})
-    if use_loss != 'AAMLoss':
-        raise NotImplementedError(f'{use_loss} 尚未在 B200 路径实现 (only AAMLoss is implemented)')
-    mod = importlib.import_module(__name__)
-    loss = getattr(mod, use_loss)(**loss_args)
-    logger.info(f'成功创建损失函数：{use_loss}，参数为：{loss_args}')
+    name = configs.loss_conf.get('loss', 'AAMLoss')
+    kwargs = dict(configs.loss_conf.get('loss_args', {}) or {})
+    if name not in _IMPLEMENTED:
+        hint = 'exists in the reference but is not implemented on the B200 path' if name in _REFERENCE_ONLY else 'is not a known loss'
+        raise NotImplementedError(f'loss {name!r} {hint} (implemented: {sorted(_IMPLEMENTED)})')
+    loss = _IMPLEMENTED[name](**kwargs)
+    logger.info(f'loss: {name} {kwargs}')
     return loss

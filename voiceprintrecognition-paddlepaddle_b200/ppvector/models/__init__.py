@@ -1,6 +1,5 @@
-"""build_model -- reference: ppvector/models/__init__.py:15-21 (string-named factory)."""
-import importlib
-
+"""Backbone factory keyed by ``model_conf.model`` (ppvector/models/__init__.py:15-21 of the reference resolves the class name by
+reflection; here the implemented backbones are listed explicitly and the remaining reference names raise with a clear message)."""
 from loguru import logger
 
 from .campplus import CAMPPlus
@@ -8,18 +7,20 @@ from .ecapa_tdnn import EcapaTdnn
 from .eres2net import ERes2Net
 from .resnet_se import ResNetSE
 
-__all__ = ['build_model']
+__all__ = ['build_model', 'CAMPPlus', 'EcapaTdnn', 'ERes2Net', 'ResNetSE']
 
-# Models of the reference that the B200 path does not implement yet (ERes2NetV2 and the plain Res2Net / TDNN variants, "next").
-_NOT_YET = ('ERes2NetV2', 'Res2Net', 'TDNN')
+_BACKBONES = {'CAMPPlus': CAMPPlus, 'EcapaTdnn': EcapaTdnn, 'ERes2Net': ERes2Net, 'ResNetSE': ResNetSE}
+# backbones the reference also ships; not part of the accelerated path
+_REFERENCE_ONLY = ('ERes2NetV2', 'Res2Net', 'TDNN')
 
 
 def build_model(input_size, configs):
-    use_model = configs.model_conf.get('model', 'CAMPPlus')
-    model_args = configs.model_conf.get('model_args', {})
-    if use_model in _NOT_YET:
-        raise NotImplementedError(f'{use_model} 尚未在 B200 路径实现 (EcapaTdnn, ResNetSE, ERes2Net and CAMPPlus are implemented; no fallback)')
-    mod = importlib.import_module(__name__)
-    model = getattr(mod, use_model)(input_size=input_size, **model_args)
-    logger.info(f'成功创建模型：{use_model}，参数为：{model_args}')
+    name = configs.model_conf.get('model', 'CAMPPlus')
+    kwargs = dict(configs.model_conf.get('model_args', {}) or {})
+    if name not in _BACKBONES:
+        if name in _REFERENCE_ONLY:
+            raise NotImplementedError(f'{name} is not implemented on the B200 path (implemented: {sorted(_BACKBONES)}); there is no fallback')
+        raise Exception(f'unknown model {name!r}')
+    model = _BACKBONES[name](input_size=input_size, **kwargs)
+    logger.info(f'model: {name} {kwargs}')
     return model

@@ -1,0 +1,1 @@
+"""Host-side helpers: argument / config printing, attribute dictionaries, checkpoint file readers."""
