@@ -1,0 +1,121 @@
+"""CPU: host-side glue in front of and behind the hot path -- wav decoding / level normalisation / resampling
+(ppvector/data_utils/audio.py, the slice of yeaudio the reference's predict.py:189-216 and reader.py:85-104 use), checkpoint files
+(ppvector/utils/checkpoint.py: the reference saves a pickled {name: ndarray} dict, `model.pdparams`), zero-padding collate
+(collate_fn.py:5-23) and the command-line option tables."""
+import io
+import os
+import pickle
+import wave
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fbank as ofb
+from ppvector.data_utils.audio import AudioSegment, normalize_db, read_wav, resample
+from ppvector.data_utils.collate_fn import collate_fn
+from ppvector.utils.checkpoint import load_state_dict_file
+
+
+def _wav_bytes(x, sr=16000, width=2, channels=1):
+    buf = io.BytesIO()
+    with wave.open(buf, "wb") as w:
+        w.setnchannels(channels)
+        w.setsampwidth(width)
+        w.setframerate(sr)
+        if width == 2:
+            w.writeframes((np.clip(x, -1, 1) * 32767).astype("<i2").tobytes())
+        else:
+            w.writeframes(((np.clip(x, -1, 1) * 127) + 128).astype(np.uint8).tobytes())
+    return buf.getvalue()
+
+
+def test_wav_decode_paths(tmp_path):
+    g = np.random.RandomState(0)
+    x = (0.3 * g.randn(4000)).astype(np.float32)
+    raw = _wav_bytes(x)
+    y, sr = read_wav(raw)
+    assert sr == 16000 and y.dtype == np.float32 and np.abs(y - np.clip(x, -1, 1)).max() < 1e-4
+    p = tmp_path / "a.wav"
+    p.write_bytes(raw)
+    assert np.array_equal(AudioSegment.from_file(str(p)).samples, y)
+    assert np.array_equal(AudioSegment.from_bytes(raw).samples, y)
+    stereo = np.stack([x, -x], axis=1).reshape(-1)
+    ys, _ = read_wav(_wav_bytes(stereo, channels=2))
+    assert np.abs(ys).max() < 1e-4  # channels are averaged
+    y8, _ = read_wav(_wav_bytes(x, width=1))
+    assert np.abs(y8 - np.clip(x, -1, 1)).max() < 2.0 / 127
+
+
+def test_db_normalisation_matches_the_oracle_and_hits_the_target():
+    g = np.random.RandomState(1)
+    x = (0.05 * g.randn(16000)).astype(np.float32)
+    y = normalize_db(x, -20.0)
+    assert abs(10 * np.log10(np.mean(y.astype(np.float64) ** 2)) + 20.0) < 1e-4
+    assert np.abs(y - ofb.db_normalize(x, -20.0)).max() < 1e-6
+    with pytest.raises(ValueError):
+        normalize_db(np.zeros(100, np.float32), -20.0)
+    seg = AudioSegment.from_ndarray(x, 16000)
+    seg.normalize(target_db=-20)
+    assert np.array_equal(seg.samples, y) and abs(seg.duration - 1.0) < 1e-9
+
+
+def test_resample_keeps_a_tone():
+    t = np.arange(8000) / 8000.0
+    x = np.sin(2 * np.pi * 440 * t).astype(np.float32)
+    y = resample(x, 8000, 16000)
+    assert abs(len(y) - 16000) <= 1
+    t2 = np.arange(len(y)) / 16000.0
+    assert np.abs(y[200:-200] - np.sin(2 * np.pi * 440 * t2)[200:-200]).max() < 2e-2
+    assert resample(x, 16000, 16000) is x
+
+
+def test_checkpoint_readers(tmp_path):
+    sd = {"0.blocks.0.conv.conv.weight": np.arange(24, dtype=np.float32).reshape(2, 3, 4), "0.fc.conv.bias": np.ones(5, np.float32),
+          "1.weight": np.zeros((5, 7), np.float32)}
+    d = tmp_path / "best_model"
+    d.mkdir()
+    with open(d / "model.pdparams", "wb") as f:  # paddle.save of a state_dict: a pickle of {name: ndarray}
+        pickle.dump(sd, f, protocol=2)
+    got = load_state_dict_file(str(d))
+    assert set(got) == set(sd) and all(np.array_equal(got[k], sd[k]) for k in sd)
+    with open(tmp_path / "tuple.pdparams", "wb") as f:  # some paddle versions store (name, ndarray) pairs
+        pickle.dump({k: (k, v) for k, v in sd.items()}, f, protocol=2)
+    got = load_state_dict_file(str(tmp_path / "tuple.pdparams"))
+    assert all(np.array_equal(got[k], sd[k]) for k in sd)
+    np.savez(tmp_path / "model.npz", **sd)
+    assert np.array_equal(load_state_dict_file(str(tmp_path / "model.npz"))["1.weight"], sd["1.weight"])
+    torch.save({k: torch.from_numpy(v) for k, v in sd.items()}, tmp_path / "model.pt")
+    assert np.array_equal(load_state_dict_file(str(tmp_path / "model.pt"))["0.fc.conv.bias"], sd["0.fc.conv.bias"])
+    empty = tmp_path / "empty_model_dir"
+    empty.mkdir()
+    with pytest.raises(FileNotFoundError):
+        load_state_dict_file(str(empty))
+
+
+def test_collate_pads_to_the_longest():
+    a, b = torch.ones(5, 3), 2 * torch.ones(8, 3)
+    feats, labels, lens = collate_fn([(a, 4), (b, 9)])
+    assert feats.shape == (2, 8, 3) and labels.tolist() == [4, 9] and lens.tolist() == [5, 8]
+    assert torch.equal(feats[0, :5], a) and float(feats[0, 5:].abs().sum()) == 0.0 and torch.equal(feats[1], b)
+
+
+def test_cli_option_tables(capsys):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import cli_common
+    import importlib
+    opt = cli_common.parse_options("x", [("configs", str, "c.yml", "h"), ("use_gpu", bool, True, "h"), ("n", int, 3, "h"), ("m", str, None, "h")],
+                                   ["--use_gpu", "False", "--n", "7", "--m", "None"])
+    assert opt.configs == "c.yml" and opt.use_gpu is False and opt.n == 7 and opt.m is None
+    with pytest.raises(SystemExit):
+        cli_common.parse_options("x", [("use_gpu", bool, True, "h")], ["--use_gpu", "maybe"])
+    # the option names of each entry script are the reference's
+    expect = {"train": {"configs", "data_augment_configs", "use_gpu", "do_eval", "save_model_path", "log_dir", "resume_model", "pretrained_model"},
+              "eval": {"configs", "use_gpu", "save_image_path", "resume_model"},
+              "extract_features": {"configs", "save_dir", "max_duration"},
+              "infer_contrast": {"configs", "use_gpu", "audio_path1", "audio_path2", "threshold", "model_path"}}
+    for name, keys in expect.items():
+        mod = importlib.import_module(name)
+        assert {row[0] for row in mod.OPTIONS} == keys, name

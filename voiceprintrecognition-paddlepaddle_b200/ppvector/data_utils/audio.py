@@ -41,7 +41,7 @@ def resample(x, sr_from, sr_to):
 
 def normalize_db(x, target_db=-20.0, max_gain_db=300.0):
     mean_square = float(np.mean(x.astype(np.float64) ** 2))
-    rms_db = 10.0 * np.log10(max(mean_square, 1e-30))
+    rms_db = 10.0 * np.log10(mean_square) if mean_square > 0.0 else -np.inf  # digital silence cannot be normalised (gain = +inf)
     gain = target_db - rms_db
     if gain > max_gain_db:
         raise ValueError(f'无法将音频归一化到 {target_db} dB: 增益 {gain} dB 超过 max_gain_db')
