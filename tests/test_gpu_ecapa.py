@@ -155,3 +155,29 @@ def test_other_pooling_types(cuda, pooling_type, T):
     assert (1 - cos).max() < 1e-8
     with pytest.raises(Exception):
         Model(input_size=80, pooling_type="XYZ")
+
+
+@pytest.mark.parametrize("T", [9, 121, 249, 250, 376, 377])
+def test_fused_res2net_chain_equals_per_conv_path(cuda, monkeypatch, T):
+    """csrc/res2chain.cu (one utterance per CTA, operand resident in shared memory) against csrc/res2conv.cu (one launch per conv) on
+    awkward lengths: padded lengths 17, 129, 257, 258 (a last tile of one or two rows), 384 (the largest the chain takes) and 385
+    (falls back).  The two paths round x_{j+1} + y_j at different places, hence ~1e-6 and not bitwise."""
+    from ppvector.models.ecapa_tdnn import EcapaTdnn as Model
+    torch.manual_seed(0)
+    sd = Model(input_size=80).state_dict()
+    g = torch.Generator().manual_seed(1)
+    for k, v in sd.items():
+        if k.endswith("_variance"):
+            sd[k] = torch.rand(v.shape, generator=g) + 0.5
+        elif k.endswith("_mean"):
+            sd[k] = torch.randn(v.shape, generator=g) * 0.1
+    x = torch.randn(5, T, 80, generator=g).to(cuda)
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("PPV_RES2_CHAIN", flag)
+        m = Model(input_size=80).eval()
+        m.load_state_dict(sd)
+        m.to(cuda)
+        outs.append(m(x).double().cpu())
+    assert torch.isfinite(outs[0]).all()
+    assert (outs[0] - outs[1]).norm() / outs[1].norm() < 1e-5
