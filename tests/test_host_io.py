@@ -119,3 +119,22 @@ def test_cli_option_tables(capsys):
     for name, keys in expect.items():
         mod = importlib.import_module(name)
         assert {row[0] for row in mod.OPTIONS} == keys, name
+
+
+def test_accuracy_helpers():
+    from ppvector.utils.utils import cal_accuracy, cal_accuracy_threshold, cosin_metric
+    g = np.random.RandomState(3)
+    truth = g.rand(500) < 0.4
+    scores = np.where(truth, 0.62, 0.35) + 0.15 * g.randn(500)
+    # the reference's loop, restated
+    best_acc, best_thr = 0, 0
+    for i in range(100):
+        thr = i * 0.01
+        acc = np.mean(((scores >= thr) == truth).astype(int))
+        if acc > best_acc:
+            best_acc, best_thr = acc, thr
+    got_acc, got_thr = cal_accuracy_threshold(scores, truth.astype(int))
+    assert abs(got_acc - best_acc) < 1e-12 and abs(got_thr - best_thr) < 1e-12
+    assert abs(cal_accuracy(scores, truth, 0.5) - np.mean((scores >= 0.5) == truth)) < 1e-12
+    a, b = g.randn(192), g.randn(192)
+    assert abs(cosin_metric(a, b) - float(a @ b / np.linalg.norm(a) / np.linalg.norm(b))) < 1e-12

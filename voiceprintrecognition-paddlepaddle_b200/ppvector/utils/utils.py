@@ -57,3 +57,23 @@ def cosin_metric(x1, x2):
     """reference: utils.py:82-83 -- a single pair is host scalar math; batches go through ppvector.metric.cosine"""
     import numpy as np
     return float(np.dot(x1, x2) / (np.linalg.norm(x1) * np.linalg.norm(x2)))
+
+
+def cal_accuracy(y_score, y_true, threshold=0.5):
+    """Fraction of trials decided correctly when scores >= threshold count as 'same speaker' (reference: utils.py:73-79)."""
+    import numpy as np
+    decided = np.asarray(y_score) >= threshold
+    return float(np.mean(decided == np.asarray(y_true).astype(bool)))
+
+
+def cal_accuracy_threshold(y_score, y_true):
+    """Best accuracy over the thresholds 0.00, 0.01, ..., 0.99 and the first threshold reaching it (reference: utils.py:56-69);
+    one vectorised comparison [100, n] instead of a Python loop."""
+    import numpy as np
+    scores, truth = np.asarray(y_score), np.asarray(y_true).astype(bool)
+    grid = np.arange(100) * 0.01
+    acc = ((scores[None, :] >= grid[:, None]) == truth[None, :]).mean(axis=1)
+    best = int(np.argmax(acc))  # argmax returns the first maximum, like the reference's strict '>' update
+    if acc[best] <= 0:
+        return 0, 0
+    return float(acc[best]), float(grid[best])
