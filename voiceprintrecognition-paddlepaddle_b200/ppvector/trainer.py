@@ -139,7 +139,9 @@ class PPVectorTrainer(object):
             yield collate_fn([dataset[int(j)] for j in chunk])
 
     def train(self, save_model_path='models/', log_dir='log/', resume_model=None, pretrained_model=None, do_eval=True, max_steps=None):
-        """reference: trainer.py:281-365.  ``max_steps`` (extension) stops early -- used by the tests and the bench tool."""
+        """reference: trainer.py:281-365.  ``max_steps`` (extension) stops early -- used by the tests and the bench tool.
+        ``pretrained_model`` / ``resume_model`` restore the weights (backbone and classifier); the optimizer moments and the
+        epoch counter of a reference checkpoint (optimizer.pdopt / model.state) are not restored: training restarts its schedules."""
         import random as _random
 
         import torch.distributed as dist
