@@ -11,18 +11,24 @@ checked against something; it is NOT part of the product:
   * the product (``voiceprintrecognition-paddlepaddle_b200/ppvector``) never imports
     it and fails loudly when the CUDA library is missing.
 
-PARITY UNPINNED: the reference ships no tests, no golden
-vectors and no weights, and its arithmetic lives in un-vendored
-third-party packages that are not installable here (paddlepaddle 2.5/2.6,
-paddleaudio>=1.0.1, yeaudio>=0.0.6).  What the oracle *is* pinned against:
+PARITY PIN: the reference ships no tests, golden vectors or weights and
+PaddlePaddle is not installable here, so the pin is made in two parts:
 
-  * ``torchaudio.compliance.kaldi.fbank`` (torchaudio 2.11, present in this image) --
-    the code paddleaudio's ``compliance/kaldi.py`` was ported from -- on the five
-    wav files bundled with the reference and on seeded synthetic audio
-    (``tests/golden/fbank_*.npz``, made by ``tests/golden/make_golden.py``);
-  * ``torch.nn.functional`` fp64 evaluation of the same graph for the model;
-  * the structural known-answers the reference README prints (``paddle.summary``
-    parameter counts, README.md:303-351).
+  * MODEL / LOSS / SCHEDULE GRAPH -- pinned to the reference's own code.  ``tests/golden/make_ref_fixtures.py``
+    imports ``/root/reference/ppvector/models/{utils,pooling,ecapa_tdnn,resnet_se,eres2net,campplus,fc}.py``,
+    ``loss/aamloss.py`` and ``optimizer/scheduler.py`` UNMODIFIED under ``tests/paddle_shim`` (a paddle -> torch
+    stand-in for the ~50 Paddle calls those files make), loads this oracle's seeded weights by ``state_dict`` name and
+    records fp64 outputs (embeddings + layer taps for four backbones at T in {98, 298}, ``lengths`` / no-global-context /
+    shortcut-conv variants, pooling modules, classifier + AAMLoss forward / backward, one TRAIN-mode step with
+    gradients and running statistics, both schedules).  ``tests/test_oracle_vs_reference.py`` asserts this oracle equals
+    those outputs to 1e-10.  What remains ASSUMED is only the semantics of each Paddle op, listed one by one in
+    ``tests/paddle_shim/README.md``.
+  * FRONT ENDS -- the arithmetic lives in un-vendored packages (paddleaudio>=1.0.1, paddle.audio, yeaudio>=0.0.6), so
+    the pin is ``torchaudio.compliance.kaldi.fbank`` (torchaudio 2.11 -- the code paddleaudio's ``compliance/kaldi.py``
+    was ported from) on the five wav files bundled with the reference and on seeded synthetic audio
+    (``tests/golden/fbank_*.npz``), torchaudio's mel / DCT / ``torch.stft`` for the STFT front ends, and the reference's
+    own ``metric/metrics.py`` for EER / minDCF.  SpecAugment / dB-normalisation follow RECALLED yeaudio behaviour:
+    that part is "parity unpinned" and says so where it is used.
 
 Every function cites the reference file:line it follows (paths relative to
 /root/reference).

@@ -133,7 +133,7 @@ def attentive_stats_pool(x, W, prefix="asp", lengths=None, global_context=True, 
 
 def ecapa_forward(feats, W: Dict[str, torch.Tensor], lengths: Optional[torch.Tensor] = None,
                   dilations=(1, 2, 3, 4, 1), res2net_scale=8, taps: Optional[dict] = None, bn=batchnorm_eval, layer_taps=False,
-                  pooling_type="ASP"):
+                  pooling_type="ASP", global_context=True):
     """ecapa_tdnn.py:245-276.  feats [B,T,F] -> embedding [B,embd_dim].
 
     ``taps`` (optional dict) is filled with intermediate activations for per-layer
@@ -156,7 +156,7 @@ def ecapa_forward(feats, W: Dict[str, torch.Tensor], lengths: Optional[torch.Ten
     if taps is not None:
         taps["mfa"] = x
     if pooling_type == "ASP":
-        x = attentive_stats_pool(x, W, "asp", lengths, bn=bn)
+        x = attentive_stats_pool(x, W, "asp", lengths, global_context=global_context, bn=bn)
         if taps is not None:
             taps["asp"] = x
         x = bn(x, W, "asp_bn.norm")
@@ -184,7 +184,7 @@ def ecapa_forward(feats, W: Dict[str, torch.Tensor], lengths: Optional[torch.Ten
 # ----------------------------------------------------------------------------------------------
 def ecapa_param_shapes(input_size=80, embd_dim=192, channels=(512, 512, 512, 512, 1536),
                        kernel_sizes=(5, 3, 3, 3, 1), attention_channels=128, res2net_scale=8,
-                       se_channels=128, pooling_type="ASP"):
+                       se_channels=128, pooling_type="ASP", global_context=True):
     """Name -> shape for every tensor in the reference EcapaTdnn state_dict (ecapa_tdnn.py:145-243)."""
     S = {}
 
@@ -215,7 +215,7 @@ def ecapa_param_shapes(input_size=80, embd_dim=192, channels=(512, 512, 512, 512
     C = channels[-1]
     tdnn("mfa", C, C, kernel_sizes[-1])
     if pooling_type == "ASP":
-        tdnn("asp.tdnn", 3 * C, attention_channels, 1)
+        tdnn("asp.tdnn", 3 * C if global_context else C, attention_channels, 1)  # pooling.py:75-78
         conv("asp.conv.conv", attention_channels, C, 1)
         bn("asp_bn.norm", 2 * C)
         conv("fc.conv", 2 * C, embd_dim, 1)
