@@ -108,8 +108,8 @@ class ConvParams(nn.Module):
         fan_in = cin
         for d in k:
             fan_in *= d
-        bound = 1.0 / fan_in ** 0.5
-        self.weight = nn.Parameter(torch.empty(cout, cin, *k).uniform_(-bound, bound))
+        # paddle.nn.Conv1D / Conv2D default initializer: Normal(0, sqrt(2 / fan_in)), bias 0
+        self.weight = nn.Parameter(torch.empty(cout, cin, *k).normal_(0.0, (2.0 / fan_in) ** 0.5))
         self.bias = nn.Parameter(torch.zeros(cout))
 
 
@@ -129,7 +129,7 @@ class LinearParams(nn.Module):
 
     def __init__(self, cin, cout):
         super().__init__()
-        bound = 1.0 / cin ** 0.5
+        bound = (6.0 / (cin + cout)) ** 0.5  # paddle.nn.Linear default: Xavier uniform, bias 0
         self.weight = nn.Parameter(torch.empty(cin, cout).uniform_(-bound, bound))
         self.bias = nn.Parameter(torch.zeros(cout))
 

@@ -3,29 +3,19 @@
 The module tree and parameter names equal the reference's Paddle ``state_dict`` (``blocks.0.conv.conv.weight``,
 ``blocks.1.res2net_block.blocks.3.norm.norm._variance`` ...), so reference checkpoints map 1:1.  The modules
 hold parameters only; ``forward`` is ONE call into libppv_b200 (``ppv_model_forward``): tcgen05/TMA gather-GEMMs
-with fused bias/ReLU/BatchNorm epilogues plus the SE / ASP reductions (csrc/ecapa.cu).  Eval mode only
-(training kernels are SURVEY.md §8 row a11, not built yet); there is no torch fallback.
+with fused bias/ReLU/BatchNorm epilogues plus the SE / ASP reductions (csrc/ecapa.cu).  This module is the eval-mode
+forward; the training step runs through ppvector/train_engine.py on the same parameter names.
+There is no torch fallback.
 """
 import ctypes as C
-import math
 
 import torch
 from torch import nn
 
 from ppvector import _lib
-from ppvector.models._native import BNParams, ConvParams, Empty
+from ppvector.models._native import BNParams, ConvParams, Empty, NativeBackbone
 
 __all__ = ['EcapaTdnn']
-
-
-class _ConvParams(nn.Module):
-    """Parameter holder named like paddle.nn.Conv1D (weight [Cout,Cin,k], bias [Cout])."""
-
-    def __init__(self, cin, cout, k):
-        super().__init__()
-        bound = 1.0 / math.sqrt(cin * k)
-        self.weight = nn.Parameter(torch.empty(cout, cin, k).uniform_(-bound, bound))
-        self.bias = nn.Parameter(torch.zeros(cout))
 
 
 class Conv1d(nn.Module):
@@ -34,18 +24,7 @@ class Conv1d(nn.Module):
     def __init__(self, in_channels, out_channels, kernel_size, dilation=1):
         super().__init__()
         self.kernel_size, self.dilation = kernel_size, dilation
-        self.conv = _ConvParams(in_channels, out_channels, kernel_size)
-
-
-class _BNParams(nn.Module):
-    """Parameter holder named like paddle.nn.BatchNorm1D (weight, bias, _mean, _variance)."""
-
-    def __init__(self, c):
-        super().__init__()
-        self.weight = nn.Parameter(torch.ones(c))
-        self.bias = nn.Parameter(torch.zeros(c))
-        self.register_buffer('_mean', torch.zeros(c))
-        self.register_buffer('_variance', torch.ones(c))
+        self.conv = ConvParams(in_channels, out_channels, kernel_size)
 
 
 class BatchNorm1d(nn.Module):
@@ -53,7 +32,7 @@ class BatchNorm1d(nn.Module):
 
     def __init__(self, input_size):
         super().__init__()
-        self.norm = _BNParams(input_size)
+        self.norm = BNParams(input_size)
 
 
 class TDNNBlock(nn.Module):
@@ -118,14 +97,14 @@ class SelfAttentivePooling(nn.Module):
         self.linear2 = ConvParams(bottleneck_dim, in_dim, 1)
 
 
-class EcapaTdnn(nn.Module):
+class EcapaTdnn(NativeBackbone):
     _POOLING = {"ASP": _lib.PPV_POOL_ASP, "SAP": _lib.PPV_POOL_SAP, "TAP": _lib.PPV_POOL_TAP, "TSP": _lib.PPV_POOL_TSP}
 
     def __init__(self, input_size, embd_dim=192, pooling_type="ASP", activation=None,
                  channels=[512, 512, 512, 512, 1536], kernel_sizes=[5, 3, 3, 3, 1], dilations=[1, 2, 3, 4, 1],
                  attention_channels=128, res2net_scale=8, se_channels=128, global_context=True,
                  precision='bf16x3'):
-        super().__init__()
+        super().__init__(precision)
         assert len(channels) == len(kernel_sizes) == len(dilations) == 5
         if pooling_type not in self._POOLING:
             raise Exception(f'没有{pooling_type}池化层！')  # ecapa_tdnn.py:242-243
@@ -156,83 +135,16 @@ class EcapaTdnn(nn.Module):
             self.asp = Empty()
             self.asp_bn = BNParams(cat_channels * 2)
             self.fc = Conv1d(cat_channels * 2, embd_dim, 1)
-        self.precision = precision
-        self._handle = None
-        self._ws = None
 
-    # ---- C-ABI plumbing -------------------------------------------------------------------------------------
-    def _prec_code(self):
-        return {'bf16x3': _lib.PPV_PREC_BF16X3, 'bf16': _lib.PPV_PREC_BF16}[self.precision]
-
-    def invalidate(self):
-        """Drop the device-side copy of the weights (call after changing parameters / load_state_dict)."""
-        if self._handle is not None:
-            _lib.load().ppv_model_destroy(self._handle)
-            self._handle = None
-
-    def load_state_dict(self, *a, **k):
-        r = super().load_state_dict(*a, **k)
-        self.invalidate()
-        return r
-
-    def _get_handle(self):
-        if self._handle is not None:
-            return self._handle
-        lib = _lib.load()
+    def _native_cfg(self):
         cfg = _lib.EcapaCfg()
-        lib.ppv_ecapa_default_cfg(C.byref(cfg))
+        _lib.load().ppv_ecapa_default_cfg(C.byref(cfg))
         cfg.input_size, cfg.embd_dim = self.input_size, self.embd_dim
         for i in range(5):
             cfg.channels[i], cfg.kernel_sizes[i], cfg.dilations[i] = self.channels[i], self.kernel_sizes[i], self.dilations[i]
         cfg.attention_channels, cfg.res2net_scale, cfg.se_channels = self.attention_channels, self.res2net_scale, self.se_channels
-        cfg.precision = self._prec_code()
         cfg.pooling = self._POOLING[self.pooling_type]
-        h = C.c_void_p()
-        _lib.check(lib.ppv_model_create(_lib.PPV_MODEL_ECAPA_TDNN, C.byref(cfg), C.byref(h)), 'ppv_model_create')
-        for name, t in self.state_dict().items():
-            t = t.detach().to(torch.float32).contiguous()
-            shape = (C.c_int64 * t.dim())(*t.shape)
-            _lib.check(lib.ppv_model_load_weight(h, name.encode(), C.c_void_p(t.data_ptr()), shape, t.dim()),
-                       f'ppv_model_load_weight({name})')
-        _lib.check(lib.ppv_model_finalize(h), 'ppv_model_finalize')
-        self._handle = h
-        return h
-
-    def set_precision(self, precision: str):
-        self.precision = precision
-        if self._handle is not None:
-            _lib.check(_lib.load().ppv_model_set_precision(self._handle, self._prec_code()), 'ppv_model_set_precision')
-
-    def _workspace(self, B, T, device):
-        need = _lib.load().ppv_model_workspace_bytes(self._get_handle(), B, T)
-        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=device)
-        return self._ws
-
-    def __del__(self):
-        try:
-            self.invalidate()
-        except Exception:
-            pass
-
-    # ---- the reference surface ------------------------------------------------------------------------------
-    def forward(self, x, lengths=None):
-        """reference: ecapa_tdnn.py:245-276.  x [N, time, freq] float32 CUDA -> [N, embd_dim]."""
-        if lengths is not None:
-            raise NotImplementedError('lengths masking is never used by the reference callers and is not implemented')
-        if self.training:
-            raise _lib.PPVError('EcapaTdnn on B200 implements the eval-mode forward only; call .eval()')
-        _lib.require_cuda(x, 'x')
-        x = x.to(torch.float32).contiguous()
-        B, T, F = x.shape
-        assert F == self.input_size
-        with torch.cuda.device(x.device):
-            h = self._get_handle()
-            ws = self._workspace(B, T, x.device)
-            emb = torch.empty((B, self.embd_dim), dtype=torch.float32, device=x.device)
-            _lib.check(_lib.load().ppv_model_forward(h, _lib.ptr(x), B, T, _lib.ptr(emb), C.c_void_p(ws.data_ptr()),
-                                                      ws.numel(), _lib.current_stream()), 'ppv_model_forward')
-        return emb
+        return _lib.PPV_MODEL_ECAPA_TDNN, cfg
 
     def forward_wav(self, featurizer, waveforms, input_lens_ratio=None):
         """Fused waveform -> embedding path (``ppv_model_forward_wav``): equals
