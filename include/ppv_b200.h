@@ -139,6 +139,7 @@ typedef struct {
     int se_channels;        /* 128 */
     int precision;          /* PPV_PREC_* */
     int pooling;            /* PPV_POOL_*: ecapa_tdnn.py:212-241 pooling_type */
+    int global_context;     /* 1 (default): ASP attends over [x; mean; std] (pooling.py:104-107); 0: over x alone */
 } ppv_ecapa_cfg;
 
 void ppv_ecapa_default_cfg(ppv_ecapa_cfg* cfg);
@@ -194,6 +195,11 @@ size_t ppv_model_workspace_bytes(const ppv_model_t* h, int B, int T);
 /* feat [B,T,input_size] fp32 (AudioFeaturizer output) -> emb [B,embd_dim] fp32. */
 int ppv_model_forward(ppv_model_t* h, const float* feat, int B, int T, float* emb, void* ws, size_t ws_bytes,
                       void* stream);
+/* ECAPA-TDNN with the reference's optional `lengths` argument (ecapa_tdnn.py:245; relative lengths in (0,1], device fp32 [B]):
+ * SEBlock squeezes (ecapa_tdnn.py:71-75) and AttentiveStatisticsPooling pools / masks its softmax (pooling.py:96-115) over the first
+ * #{t : t < lengths[b] * T} frames of each utterance.  lengths == NULL is ppv_model_forward. */
+int ppv_model_forward_lengths(ppv_model_t* h, const float* feat, const float* lengths, int B, int T, float* emb, void* ws,
+                              size_t ws_bytes, void* stream);
 /* Fused front end + model: wav [B,L] fp32 -> emb [B,embd_dim]; the Fbank features go straight into the
  * first conv's operand layout and never exist as [B,T,F] fp32.  lens_ratio as ppv_fbank_forward. */
 int ppv_model_forward_wav(ppv_model_t* h, ppv_fbank_t* fb, const float* wav, const float* lens_ratio, int B, int L,

@@ -196,10 +196,26 @@ def test_trainer_train_runs_the_cuda_step(cuda, wavs, cfg, tmp_path):
     history = tr.train(save_model_path=save, do_eval=True)
     assert len(history) == 4 and all(np.isfinite(history)) and history[0] > 0.5  # 10 utterances / batch 4, drop_last: 2 steps x 2 epochs
     assert tr.engine.step_count == 4 and float(tr.engine.exp_avg_sq.abs().sum()) > 0
-    ck = torch.load(os.path.join(save, "model.pt"))
+    # the reference's checkpoint layout (utils/checkpoint.py:104-159): <model>_<feature>/{epoch_N, last_model, best_model}
+    import json
+    root = os.path.join(save, "EcapaTdnn_Fbank")
+    assert sorted(os.listdir(root)) == ["best_model", "epoch_1", "epoch_2", "last_model"]
+    ck = torch.load(os.path.join(root, "last_model", "model.pt"))
     assert "0.blocks.0.conv.conv.weight" in ck and ck["1.weight"].shape == (192, 3)
-    eer, min_dcf, thr = PPVectorTrainer(cfg, use_gpu=True).evaluate(resume_model=save)
+    state = json.load(open(os.path.join(root, "last_model", "model.state")))
+    assert state["last_epoch"] == 2 and state["model_conf.model"] == "EcapaTdnn" and "eer" in state and "margin" in state
+    opt = torch.load(os.path.join(root, "last_model", "optimizer.pt"))
+    assert opt["step_count"] == 4 and torch.equal(opt["exp_avg_sq"], tr.engine.exp_avg_sq.cpu())
+    eer, min_dcf, thr = PPVectorTrainer(cfg, use_gpu=True).evaluate(resume_model=os.path.join(root, "best_model"))
     assert 0.0 <= eer <= 1.0 and np.isfinite(thr)
+    # resume: a third epoch continues from last_model -- Adam moments, step count, LR / margin schedule positions and the epoch
+    cfg3 = copy.deepcopy(cfg)
+    cfg3["train_conf"]["max_epoch"] = 3
+    tr3 = PPVectorTrainer(cfg3, use_gpu=True, data_augment_configs=aug)
+    h3 = tr3.train(save_model_path=save, do_eval=False)
+    assert len(h3) == 2 and tr3.engine.step_count == 6 and tr3.train_step == 6
+    assert json.load(open(os.path.join(root, "last_model", "model.state")))["last_epoch"] == 3
+    assert not os.path.exists(os.path.join(root, "epoch_0")) and os.path.exists(os.path.join(root, "epoch_3"))
     cfg2 = copy.deepcopy(cfg)
     cfg2["model_conf"]["model"] = "ResNetSE"
     with pytest.raises(NotImplementedError):

@@ -121,9 +121,10 @@ def test_bf16_fast_mode_is_close_but_flagged(cuda, W64):
     assert (1 - cos).max() < 1e-3  # fast mode: NOT within the 1e-4 score tolerance, hence not the default
 
 
-def test_full_size_properties(cuda, model):
+def test_full_size_properties(cuda, model, W64):
     """BASELINE config 2 (256 x 298 frames): utterances are independent -- a row of the big batch equals the
-    same utterance run alone (bit-exact: same kernels, same per-row arithmetic); embeddings finite."""
+    same utterance run alone (bit-exact: same kernels, same per-row arithmetic); embeddings finite; and a DIRECT comparison of
+    8 rows of the full-size batch with the fp64 oracle (both ends of the batch, both waves of the one-CTA-per-utterance kernels)."""
     gi = torch.Generator().manual_seed(1000)
     f = torch.randn(256, 298, 80, generator=gi).to(cuda)
     emb = model(f)
@@ -131,6 +132,15 @@ def test_full_size_properties(cuda, model):
     for b in (0, 100, 255):
         single = model(f[b:b + 1])
         assert torch.equal(single, emb[b:b + 1])
+    rows = [0, 1, 100, 147, 148, 200, 254, 255]
+    ref = oe.ecapa_forward(f[rows].double().cpu(), W64)
+    got = emb[rows].double().cpu()
+    rel = (got - ref).norm(dim=1) / ref.norm(dim=1)
+    assert rel.max() < 1e-4, rel
+    assert (1 - torch.nn.functional.cosine_similarity(got, ref)).max() < 1e-8
+    s_ref = oh.cosine_matrix(ref.numpy(), ref.numpy())
+    s_got = oh.cosine_matrix(got.numpy(), got.numpy())
+    assert np.abs(s_ref - s_got).max() < COS_TOL
 
 
 @pytest.mark.parametrize("pooling_type", ["SAP", "TAP", "TSP"])
@@ -163,14 +173,9 @@ def test_fused_res2net_chain_equals_per_conv_path(cuda, monkeypatch, T):
     awkward lengths: padded lengths 17, 129, 257, 258 (a last tile of one or two rows), 384 (the largest the chain takes) and 385
     (falls back).  The two paths round x_{j+1} + y_j at different places, hence ~1e-6 and not bitwise."""
     from ppvector.models.ecapa_tdnn import EcapaTdnn as Model
-    torch.manual_seed(0)
-    sd = Model(input_size=80).state_dict()
+    from ppvector.utils.init import seeded_state_dict
+    sd = seeded_state_dict(Model(input_size=80), seed=1)
     g = torch.Generator().manual_seed(1)
-    for k, v in sd.items():
-        if k.endswith("_variance"):
-            sd[k] = torch.rand(v.shape, generator=g) + 0.5
-        elif k.endswith("_mean"):
-            sd[k] = torch.randn(v.shape, generator=g) * 0.1
     x = torch.randn(5, T, 80, generator=g).to(cuda)
     outs = []
     for flag in ("1", "0"):
@@ -181,3 +186,48 @@ def test_fused_res2net_chain_equals_per_conv_path(cuda, monkeypatch, T):
         outs.append(m(x).double().cpu())
     assert torch.isfinite(outs[0]).all()
     assert (outs[0] - outs[1]).norm() / outs[1].norm() < 1e-5
+
+
+@pytest.mark.parametrize("T", [98, 298])
+def test_lengths_masking_matches_reference_fixture(cuda, model, W64, golden_dir, T):
+    """`lengths` (ecapa_tdnn.py:245; SEBlock :71-75, ASP pooling.py:96-115): the CUDA path against the oracle, and at T = 98 against
+    the embedding the REFERENCE's own code produced (tests/golden/ref_models.npz, lengths = [1.0, 0.6])."""
+    gi = torch.Generator().manual_seed(1000 + T)
+    f = torch.randn(2, T, 80, generator=gi, dtype=torch.float64)
+    f = f - f.mean(1, keepdim=True)
+    lens = torch.tensor([1.0, 0.6], dtype=torch.float64)
+    ref = oe.ecapa_forward(f, W64, lengths=lens)
+    emb = model(f.float().to(cuda), lengths=lens.float().to(cuda)).double().cpu()
+    rel = (emb - ref).norm(dim=1) / ref.norm(dim=1)
+    assert rel.max() < 1e-4, rel
+    assert (1 - torch.nn.functional.cosine_similarity(emb, ref)).max() < 1e-8
+    if T == 98:
+        g = np.load(f"{golden_dir}/ref_models.npz")
+        want = torch.from_numpy(g["ecapa_T98_lengths_emb"])
+        assert ((emb - want).norm(dim=1) / want.norm(dim=1)).max() < 1e-4
+    # row 0 has lengths 1.0: identical to the un-masked forward; row 1 differs
+    plain = model(f.float().to(cuda)).double().cpu()
+    assert torch.allclose(plain[0], emb[0], rtol=0, atol=1e-6)
+    assert (plain[1] - emb[1]).abs().max() > 1e-3
+    # odd ratios: the count is #{t : t < ratio * T} (float compare, utils.py:8-19)
+    for r in (0.013, 0.5, 0.999):
+        lens = torch.tensor([r, 1.0], dtype=torch.float64)
+        ref = oe.ecapa_forward(f, W64, lengths=lens)
+        emb = model(f.float().to(cuda), lengths=lens.float().to(cuda)).double().cpu()
+        assert ((emb - ref).norm(dim=1) / ref.norm(dim=1)).max() < 1e-4, r
+
+
+def test_asp_without_global_context(cuda, golden_dir):
+    """AttentiveStatisticsPooling(global_context=False) (pooling.py:77-78, 108-109) against the oracle and the reference-code fixture."""
+    Wg = oe.make_ecapa_weights(seed=1000, dtype=torch.float64, global_context=False)
+    m = EcapaTdnn(input_size=80, global_context=False).eval()
+    m.load_state_dict({k: v.float() for k, v in Wg.items()}, strict=True)
+    m.to(cuda)
+    gi = torch.Generator().manual_seed(1000 + 98)
+    f = torch.randn(2, 98, 80, generator=gi, dtype=torch.float64)
+    f = f - f.mean(1, keepdim=True)
+    ref = oe.ecapa_forward(f, Wg, global_context=False)
+    emb = m(f.float().to(cuda)).double().cpu()
+    assert ((emb - ref).norm(dim=1) / ref.norm(dim=1)).max() < 1e-4
+    want = torch.from_numpy(np.load(f"{golden_dir}/ref_models.npz")["ecapa_T98_noctx_emb"])
+    assert ((emb - want).norm(dim=1) / want.norm(dim=1)).max() < 1e-4

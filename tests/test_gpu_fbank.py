@@ -77,3 +77,8 @@ def test_full_size_properties(cuda, fz):
     assert out.mean(1).abs().max().item() < 2e-5
     for b in (0, 17, 255):
         assert torch.equal(fz(x[b]), out[b:b + 1])
+    # direct oracle comparison of 8 rows of the full-size batch (first / last work items, both ends of the batch)
+    rows = [0, 1, 63, 100, 127, 200, 254, 255]
+    ref = ofb.audio_featurizer_fbank(x[rows].cpu().numpy(), None, dtype=np.float64, n_mels=80)
+    d = np.abs(out[rows].cpu().numpy() - ref)
+    assert d.max() < TOL_MAX and d.mean() < TOL_MEAN, (d.max(), d.mean())

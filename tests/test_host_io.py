@@ -138,3 +138,63 @@ def test_accuracy_helpers():
     assert abs(cal_accuracy(scores, truth, 0.5) - np.mean((scores >= 0.5) == truth)) < 1e-12
     a, b = g.randn(192), g.randn(192)
     assert abs(cosin_metric(a, b) - float(a @ b / np.linalg.norm(a) / np.linalg.norm(b))) < 1e-12
+
+
+def _riff_bytes(samples_f64, sr, tag, bits, ch=1, extensible=False):
+    """Build a RIFF/WAVE file in memory (test helper): tag 1 = PCM, 3 = IEEE float."""
+    import struct
+    x = np.asarray(samples_f64, dtype=np.float64).reshape(-1, ch)
+    if tag == 3:
+        raw = x.astype("<f4" if bits == 32 else "<f8").tobytes()
+    elif bits == 8:
+        raw = (np.round(x * 128.0) + 128).clip(0, 255).astype(np.uint8).tobytes()
+    elif bits == 16:
+        raw = np.round(x * 32768.0).clip(-32768, 32767).astype("<i2").tobytes()
+    elif bits == 24:
+        v = np.round(x * 8388608.0).clip(-8388608, 8388607).astype(np.int64).reshape(-1)
+        v = np.where(v < 0, v + (1 << 24), v)
+        raw = np.stack([v & 255, (v >> 8) & 255, (v >> 16) & 255], axis=1).astype(np.uint8).tobytes()
+    else:
+        raw = np.round(x * 2147483648.0).clip(-2147483648, 2147483647).astype("<i4").tobytes()
+    block = ch * bits // 8
+    if extensible:
+        guid_tail = bytes.fromhex("000000001000800000aa00389b71")
+        fmt = struct.pack("<HHIIHH", 0xFFFE, ch, sr, sr * block, block, bits) + struct.pack("<HHI", 22, bits, 0) + struct.pack("<H", tag) + guid_tail
+    else:
+        fmt = struct.pack("<HHIIHH", tag, ch, sr, sr * block, block, bits)
+    body = b"WAVE" + b"fmt " + struct.pack("<I", len(fmt)) + fmt + b"LIST" + struct.pack("<I", 4) + b"abcd" + b"data" + struct.pack("<I", len(raw)) + raw
+    return b"RIFF" + struct.pack("<I", len(body)) + body
+
+
+@pytest.mark.parametrize("tag,bits,tol", [(1, 8, 1 / 100), (1, 16, 1e-4), (1, 24, 1e-6), (1, 32, 1e-7), (3, 32, 1e-7), (3, 64, 1e-7)])
+def test_wav_decoder_formats(tag, bits, tol):
+    """AudioSegment.from_file / from_bytes read what yeaudio reads through soundfile for WAV: integer PCM 8-32 bit (incl. packed
+    24-bit), IEEE float, WAVE_FORMAT_EXTENSIBLE headers, extra chunks, multi-channel (averaged); other containers raise by name."""
+    from ppvector.data_utils.audio import AudioSegment, read_wav
+    rng = np.random.default_rng(bits + tag)
+    x = rng.uniform(-0.9, 0.9, 1000)
+    for ext in (False, True):
+        y, sr = read_wav(_riff_bytes(x, 22050, tag, bits, extensible=ext))
+        assert sr == 22050 and y.dtype == np.float32 and y.shape == (1000,)
+        assert np.abs(y - x).max() < tol
+    st = rng.uniform(-0.5, 0.5, (500, 2))
+    y, _ = read_wav(_riff_bytes(st, 16000, tag, bits, ch=2))
+    assert np.abs(y - st.mean(1)).max() < 2 * tol
+    seg = AudioSegment.from_bytes(_riff_bytes(x, 16000, tag, bits))
+    assert seg.sample_rate == 16000 and abs(seg.duration - 1000 / 16000) < 1e-9
+
+
+def test_wav_decoder_rejects_other_containers_by_name(tmp_path):
+    from ppvector.data_utils.audio import read_wav
+    try:
+        import soundfile  # noqa: F401
+        pytest.skip("soundfile installed: other containers are decoded by it")
+    except ImportError:
+        pass
+    with pytest.raises(ValueError, match="FLAC"):
+        read_wav(b"fLaC" + bytes(64))
+    with pytest.raises(ValueError, match="format tag"):
+        import struct
+        fmt = struct.pack("<HHIIHH", 0x0055, 1, 16000, 2000, 1, 0)
+        body = b"WAVE" + b"fmt " + struct.pack("<I", 16) + fmt + b"data" + struct.pack("<I", 4) + bytes(4)
+        read_wav(b"RIFF" + struct.pack("<I", len(body)) + body)

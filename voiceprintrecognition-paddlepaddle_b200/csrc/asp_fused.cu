@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(384, 1) asp_fused_kernel(const __grid_constant
             const int64_t goff = int64_t(b) * p.gstat.ld + c;
             const float g = __bfloat162float(p.gstat.hi()[goff]) + __bfloat162float(p.gstat.lo()[goff]);
             float m = -INFINITY, S0 = 0.f, S1 = 0.f, S2 = 0.f;
+            const int Tb = p.nvalid ? max(1, min(p.T, p.nvalid[b])) : p.T;  // masked frames: softmax weight exactly 0
             for (int ft = 0; ft < ntiles; ++ft) {
                 mbar_wait(b_full(stage), phase);  // acquire the TMA-written x tile directly (already complete by now)
                 mbar_wait(tfull(acc), acc_phase);
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(384, 1) asp_fused_kernel(const __grid_constant
                     __syncwarp();
                     tmem_ld32(t_addr + ch * 32, v);
                     tmem_ld_wait();
-                    const int nvalid = min(32, p.T - t0);  // warp-uniform
+                    const int nvalid = min(32, Tb - t0);  // warp-uniform
                     if (nvalid > 0) {
                         // chunk max as a 4-way tree (the serial fmax chain is latency-bound with 2 warps per scheduler)
                         float cm4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -322,6 +323,7 @@ int asp_fused_build(AspFusedParams* p, const Planes& W, const Planes& att, const
     p->C = C;
     p->K = K;
     p->eps = eps;
+    p->nvalid = nullptr;
     return PPV_OK;
 }
 

@@ -140,6 +140,7 @@ void ppv_ecapa_default_cfg(ppv_ecapa_cfg* c) {
     c->se_channels = 128;
     c->precision = PPV_PREC_BF16X3;
     c->pooling = PPV_POOL_ASP;
+    c->global_context = 1;
 }
 
 void ppv_eres2net_default_cfg(ppv_eres2net_cfg* c) {
@@ -240,6 +241,14 @@ int ppv_model_forward(ppv_model_t* h, const float* feat, int B, int T, float* em
     if (h->eres) return eres2net_forward(h->eres, feat, B, T, emb, ws, ws_bytes, static_cast<cudaStream_t>(stream));
     if (h->campp) return campplus_forward(h->campp, feat, B, T, emb, ws, ws_bytes, static_cast<cudaStream_t>(stream));
     return ecapa_forward(h->ecapa, feat, nullptr, nullptr, nullptr, B, T, 0, emb, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+    PPV_GUARD_END
+}
+int ppv_model_forward_lengths(ppv_model_t* h, const float* feat, const float* lengths, int B, int T, float* emb, void* ws, size_t ws_bytes,
+                              void* stream) {
+    PPV_GUARD_BEGIN
+    PPV_REQUIRE(h && feat && emb, "ppv_model_forward_lengths: null argument");
+    if (!h->ecapa) return fail(PPV_EUNSUPPORTED, "ppv_model_forward_lengths: only EcapaTdnn.forward takes lengths in the reference");
+    return ecapa_forward(h->ecapa, feat, nullptr, nullptr, nullptr, B, T, 0, emb, ws, ws_bytes, static_cast<cudaStream_t>(stream), lengths);
     PPV_GUARD_END
 }
 int ppv_model_forward_wav(ppv_model_t* h, ppv_fbank_t* fb, const float* wav, const float* lens_ratio, int B, int L, float* emb,

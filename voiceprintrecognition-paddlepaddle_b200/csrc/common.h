@@ -204,6 +204,7 @@ struct AspFusedParams {
     float* out_raw;      // [B, 2C] fp32 before asp_bn (tap)
     int B, T, P, Tp, C, K;
     float eps;
+    const int* nvalid;  // optional [B]: frames t >= nvalid[b] get attention weight 0 (`lengths`, pooling.py:112-115); set per launch
 };
 
 int asp_fused_build(AspFusedParams* p, const Planes& W, const Planes& att, const Planes& x, const Planes& gstat, const float* bn_scale,
@@ -213,7 +214,8 @@ int asp_fused_launch(const AspFusedParams& p, int precision, int num_sms, cudaSt
 // ---- other kernels (elementwise.cu) ---------------------------------------------------------------
 int launch_pack_features(const float* feat, int B, int T, int F, const Planes& out, int P, int Tp, cudaStream_t st);
 int launch_colstats(const Planes& x, int col0, int C, int B, int T, int P, int Tp, int mode, float eps, float* out_f32,
-                    const Planes& out_pl, cudaStream_t st, float inv_count = 0.f);
+                    const Planes& out_pl, cudaStream_t st, float inv_count = 0.f, const int* nvalid = nullptr);
+int launch_lengths_to_counts(const float* lengths, int B, int T, int* nvalid, cudaStream_t st);
 int launch_se_scale_res(const Planes& z, const float* scale, const Planes& res, int rc0, const Planes& out, int oc0, int C,
                         int Tp, int64_t rows, int num_sms, cudaStream_t st, int relu = 0, float relu_max = 0.f);
 int launch_asp_pool(const float* logits, int64_t lg_ld, const Planes& x, int C, int B, int T, int P, int Tp, float eps,
@@ -250,7 +252,7 @@ int ecapa_set_precision(EcapaModel* m, int precision);
 int ecapa_embd_dim(const EcapaModel* m);
 size_t ecapa_workspace_bytes(const EcapaModel* m, int B, int T);
 int ecapa_forward(EcapaModel* m, const float* feat, Fbank* fb, const float* wav, const float* lens_ratio, int B, int T, int L,
-                  float* emb, void* ws, size_t ws_bytes, cudaStream_t st);
+                  float* emb, void* ws, size_t ws_bytes, cudaStream_t st, const float* lengths = nullptr);
 int ecapa_read_tap(EcapaModel* m, const char* name, float* out, size_t out_elems, cudaStream_t st);
 int ecapa_profile(EcapaModel* m, int enable);
 int ecapa_profile_read(EcapaModel* m, double* gemm_ms, double* other_ms, int64_t* gemm_launches, int64_t* other_launches);

@@ -78,6 +78,7 @@ struct EcapaModel {
     Planes bufs[B_COUNT];
     float *se_mean = nullptr, *se_scale = nullptr, *fold_out = nullptr, *logits = nullptr, *pooled_raw = nullptr,
           *raw_logmel = nullptr, *emb_out = nullptr;
+    int* nvalid = nullptr;  // [B] valid-frame counts of the current forward (`lengths`), workspace
     int Tp = 0;
     // profiling (bench.py roofline): CUDA events around every launch group of the forward
     bool prof_on = false;
@@ -327,9 +328,11 @@ int ecapa_finalize(EcapaModel* m) {
         return true;
     };
     if (pooling == PPV_POOL_ASP) {
-    // ASP attention TDNN: weight [A, 3*C3, 1] split into the x part (cols 0..C3) and the [mean;std] part
-    ok = ok && conv_layer(&m->att1, "asp.tdnn.conv.conv", A, 3 * C3, 1, {{B_MFA, 0, C3, 0, 0, C3, 0}}, "asp.tdnn.norm.norm", true);
-    if (ok) {
+    // ASP attention TDNN: weight [A, 3*C3, 1] split into the x part (cols 0..C3) and the [mean;std] part;
+    // global_context = False (pooling.py:77-78, 108-109): the TDNN sees x alone, weight [A, C3, 1], no per-utterance bias
+    const int ctx = m->cfg.global_context ? 3 : 1;
+    ok = ok && conv_layer(&m->att1, "asp.tdnn.conv.conv", A, ctx * C3, 1, {{B_MFA, 0, C3, 0, 0, C3, 0}}, "asp.tdnn.norm.norm", true);
+    if (ok && m->cfg.global_context) {
         const HostW* hw = f.get("asp.tdnn.conv.conv.weight", {A, 3 * C3, 1});
         size_t off;
         f.put_conv(&m->fold, hw, A, 3 * C3, 1, {{B_GSTAT, 0, 2 * C3, 0, C3, 2 * C3, 0}}, &off);
@@ -416,6 +419,7 @@ void carve(EcapaModel* m, Carver& cv, int B, int T) {
     m->pooled_raw = static_cast<float*>(cv.take(size_t(B) * 2 * C3 * 4));
     m->raw_logmel = static_cast<float*>(cv.take(size_t(B) * T * m->cfg.input_size * 4));
     m->emb_out = static_cast<float*>(cv.take(size_t(align_up(B, 128)) * m->cfg.embd_dim * 4));
+    m->nvalid = static_cast<int*>(cv.take(size_t(B) * sizeof(int)));
     m->Tp = Tp;
 }
 
@@ -581,7 +585,7 @@ static int build_plan(EcapaModel* m, int B, int T, void* ws, size_t ws_bytes, cu
         s.kind = Step::ASP_GLOBAL;
         m->steps.push_back(s);
     }
-    if (pooling == PPV_POOL_ASP) {  // fold: [B, 2*C3] . W[:, C3:3*C3]^T -> per-utterance bias [B, att]  (no conv bias here)
+    if (pooling == PPV_POOL_ASP && m->cfg.global_context) {  // fold: [B, 2*C3] . W[:, C3:3*C3]^T -> per-utterance bias [B, att]  (no conv bias here)
         Epilogue ep;
         ep.out_mode = OUT_F32;
         ep.out = m->fold_out;
@@ -595,7 +599,7 @@ static int build_plan(EcapaModel* m, int B, int T, void* ws, size_t ws_bytes, cu
         {  // ASP: attention TDNN (K = C3) + per-utterance bias -> ReLU -> BN -> tanh;  SAP: tanh(linear1(x))
             Epilogue ep = planes_out(m->bufs[B_ATT], 0, false);
             if (pooling == PPV_POOL_ASP) {
-                ep.rowgrp_bias = m->fold_out;
+                if (m->cfg.global_context) ep.rowgrp_bias = m->fold_out;
             } else {
                 ep.relu = 0;
             }
@@ -629,7 +633,7 @@ static int build_plan(EcapaModel* m, int B, int T, void* ws, size_t ws_bytes, cu
 
 // ------------------------------------------------------------------------------------------------ forward
 int ecapa_forward(EcapaModel* m, const float* feat, Fbank* fb, const float* wav, const float* lens_ratio, int B, int T, int L,
-                  float* emb, void* ws, size_t ws_bytes, cudaStream_t st) {
+                  float* emb, void* ws, size_t ws_bytes, cudaStream_t st, const float* lengths) {
     PPV_REQUIRE(m && emb, "ecapa_forward: null argument");
     if (!m->finalized) return fail(PPV_ESTATE, "ecapa_forward: call ppv_model_finalize first");
     PPV_REQUIRE(B > 0 && T > 0, "ecapa_forward: empty batch");
@@ -667,6 +671,15 @@ int ecapa_forward(EcapaModel* m, const float* feat, Fbank* fb, const float* wav,
             m->prof_used += 2;
         }
     };
+    // `lengths` (ecapa_tdnn.py:245, relative lengths in (0,1]): SEBlock squeezes and ASP pools over the first
+    // #{t : t < lengths[b] * T} frames of each utterance (ecapa_tdnn.py:71-75, pooling.py:96-115); everything else sees all T frames.
+    const int* nv = nullptr;
+    if (lengths) {
+        PPV_REQUIRE(m->cfg.pooling == PPV_POOL_ASP, "ecapa_forward: lengths is implemented for ASP pooling (the other heads ignore it in the reference)");
+        rc = launch_lengths_to_counts(lengths, B, T, m->nvalid, st);
+        if (rc) return rc;
+        nv = m->nvalid;
+    }
     prof_mark(1, true);
     if (wav) {
         rc = fbank_run(fb, wav, lens_ratio, B, L, m->raw_logmel, nullptr, m->bufs[B_FEAT], P, Tp, st);
@@ -692,7 +705,7 @@ int ecapa_forward(EcapaModel* m, const float* feat, Fbank* fb, const float* wav,
                 }
                 break;
             case Step::SE_SQUEEZE:
-                rc = launch_colstats(m->bufs[B_Z], 0, C, B, T, P, Tp, 0, 0.f, nullptr, m->bufs[B_SEM], st);
+                rc = launch_colstats(m->bufs[B_Z], 0, C, B, T, P, Tp, 0, 0.f, nullptr, m->bufs[B_SEM], st, 0.f, nv);
                 break;
             case Step::SE_SCALE: {
                 const Planes& X = (s.blk == 1) ? m->bufs[B_X0] : m->bufs[B_CAT];
@@ -701,11 +714,14 @@ int ecapa_forward(EcapaModel* m, const float* feat, Fbank* fb, const float* wav,
                 break;
             }
             case Step::ASP_GLOBAL:
-                rc = launch_colstats(m->bufs[B_MFA], 0, C3, B, T, P, Tp, 1, 1e-12f, nullptr, m->bufs[B_GSTAT], st);
+                rc = launch_colstats(m->bufs[B_MFA], 0, C3, B, T, P, Tp, 1, 1e-12f, nullptr, m->bufs[B_GSTAT], st, 0.f, nv);
                 break;
-            case Step::ASP_FUSED:
-                rc = asp_fused_launch(s.ap, m->precision, m->num_sms, st);
+            case Step::ASP_FUSED: {
+                AspFusedParams ap = s.ap;
+                ap.nvalid = nv;
+                rc = asp_fused_launch(ap, m->precision, m->num_sms, st);
                 break;
+            }
             case Step::POOL_STATS:
                 rc = launch_colstats(m->bufs[B_MFA], 0, C3, B, T, P, Tp, m->cfg.pooling == PPV_POOL_TAP ? 0 : 3, 0.f, nullptr, m->bufs[B_POOL], st);
                 break;

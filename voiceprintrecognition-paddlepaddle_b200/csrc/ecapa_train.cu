@@ -127,7 +127,8 @@ int trainer_create(const ppv_ecapa_cfg* cfg, int num_classes, Trainer** out) {
         return fail(PPV_EUNSUPPORTED, "trainer: kernel sizes must be [odd,3,3,3,1]");
     if (cfg->attention_channels % 64 || cfg->se_channels % 8 || cfg->embd_dim % 8)
         return fail(PPV_EUNSUPPORTED, "trainer: attention_channels % 64, se_channels % 8, embd_dim % 8 required");
-    if (cfg->pooling != PPV_POOL_ASP) return fail(PPV_EUNSUPPORTED, "trainer: the training step implements pooling_type ASP");
+    if (cfg->pooling != PPV_POOL_ASP || !cfg->global_context)
+        return fail(PPV_EUNSUPPORTED, "trainer: the training step implements pooling_type ASP with global_context");
     Trainer* t = new Trainer();
     t->cfg = *cfg;
     t->S = num_classes;

@@ -89,13 +89,15 @@ __device__ __forceinline__ float2 block_colsum(float2 v, float2 (*s_part)[32], i
 // Single pass with a per-channel shift K = x[first frame]: sum(x-K), sum((x-K)^2); var = (Q - S^2/T)/T.
 // Each lane owns 8 channels (one 16-byte load per plane), 4 frames per warp, 32 frames per block iteration.
 __global__ void __launch_bounds__(STAT_WARPS * 32)
-    colstats_kernel(Planes x, int col0, int C, int T, int P, int Tp, int mode, float eps, float inv_count, float* __restrict__ out_f32,
-                    Planes out_pl) {
+    colstats_kernel(Planes x, int col0, int C, int T_all, int P, int Tp, int mode, float eps, float inv_count, float* __restrict__ out_f32,
+                    Planes out_pl, const int* __restrict__ nvalid) {
     __shared__ float s_s[STAT_WARPS][64];
     __shared__ float s_q[STAT_WARPS][64];
     griddep_launch_dependents();
     griddep_wait();
     const int b = blockIdx.y;
+    // `lengths` of the reference (ecapa_tdnn.py:71-75, pooling.py:96-103): statistics over the first nvalid[b] frames only
+    const int T = nvalid ? max(1, min(T_all, nvalid[b])) : T_all;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cg = lane & 7, rsub = lane >> 3;
     const int c = col0 + blockIdx.x * 64 + cg * 8;
@@ -182,11 +184,29 @@ __global__ void __launch_bounds__(STAT_WARPS * 32)
     }
 }
 
+// nvalid[b] = #{t in [0,T): float(t) < lengths[b] * float(T)} -- the reference's length_to_mask(lengths * L, max_len=L)
+// (ppvector/models/utils.py:8-19) compares a float arange with the float product, no truncation
+__global__ void lengths_to_counts_kernel(const float* __restrict__ lengths, int B, int T, int* __restrict__ nvalid) {
+    griddep_launch_dependents();
+    griddep_wait();
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float lim = lengths[b] * float(T);
+    int n = 0;
+    for (int t = 0; t < T; ++t) n += (float(t) < lim) ? 1 : 0;
+    nvalid[b] = n;
+}
+int launch_lengths_to_counts(const float* lengths, int B, int T, int* nvalid, cudaStream_t st) {
+    PPV_PDL_OK(launch_pdl(lengths_to_counts_kernel, dim3((B + 127) / 128), dim3(128), 0, st, lengths, B, T, nvalid), "lengths_to_counts_kernel");
+    return PPV_OK;
+}
+
 int launch_colstats(const Planes& x, int col0, int C, int B, int T, int P, int Tp, int mode, float eps, float* out_f32,
-                    const Planes& out_pl, cudaStream_t st, float inv_count) {
+                    const Planes& out_pl, cudaStream_t st, float inv_count, const int* nvalid) {
     PPV_REQUIRE(C % 64 == 0 && col0 % 8 == 0 && x.ld % 8 == 0, "colstats: C % 64, col0 % 8, ld % 8 required");
     dim3 grid(C / 64, B);
-    PPV_PDL_OK(launch_pdl(colstats_kernel, grid, dim3(STAT_WARPS * 32), 0, st, x, col0, C, T, P, Tp, mode, eps, inv_count, out_f32, out_pl), "colstats_kernel");
+    PPV_PDL_OK(launch_pdl(colstats_kernel, grid, dim3(STAT_WARPS * 32), 0, st, x, col0, C, T, P, Tp, mode, eps, inv_count, out_f32, out_pl, nvalid),
+               "colstats_kernel");
     return PPV_OK;
 }
 

@@ -28,7 +28,8 @@ class FbankCfg(C.Structure):
 class EcapaCfg(C.Structure):
     _fields_ = [("input_size", C.c_int), ("embd_dim", C.c_int), ("channels", C.c_int * 5),
                 ("kernel_sizes", C.c_int * 5), ("dilations", C.c_int * 5), ("attention_channels", C.c_int),
-                ("res2net_scale", C.c_int), ("se_channels", C.c_int), ("precision", C.c_int), ("pooling", C.c_int)]
+                ("res2net_scale", C.c_int), ("se_channels", C.c_int), ("precision", C.c_int), ("pooling", C.c_int),
+                ("global_context", C.c_int)]
 
 
 class ResNetSECfg(C.Structure):
@@ -92,6 +93,7 @@ SIGNATURES = {
     "ppv_model_embd_dim": (C.c_int, [_P]),
     "ppv_model_workspace_bytes": (C.c_size_t, [_P, C.c_int, C.c_int]),
     "ppv_model_forward": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, C.c_size_t, _P]),
+    "ppv_model_forward_lengths": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, C.c_size_t, _P]),
     "ppv_model_forward_wav": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P, _P, C.c_size_t, _P]),
     "ppv_model_read_tap": (C.c_int, [_P, C.c_char_p, _P, C.c_size_t, _P]),
     "ppv_model_profile": (C.c_int, [_P, C.c_int]),

@@ -82,9 +82,8 @@ class AttentiveStatisticsPooling(nn.Module):
 
     def __init__(self, channels, attention_channels=128, global_context=True):
         super().__init__()
-        if not global_context:
-            raise NotImplementedError('ASP without global_context is not implemented on B200')
-        self.tdnn = TDNNBlock(channels * 3, attention_channels, 1, 1)
+        self.global_context = global_context
+        self.tdnn = TDNNBlock(channels * 3 if global_context else channels, attention_channels, 1, 1)  # pooling.py:75-78
         self.conv = Conv1d(attention_channels, channels, 1)
 
 
@@ -112,6 +111,7 @@ class EcapaTdnn(NativeBackbone):
         self.input_size, self.channels, self.embd_dim = input_size, list(channels), embd_dim
         self.kernel_sizes, self.dilations = list(kernel_sizes), list(dilations)
         self.attention_channels, self.res2net_scale, self.se_channels = attention_channels, res2net_scale, se_channels
+        self.global_context = bool(global_context)
         self.blocks = nn.ModuleList()
         self.blocks.append(TDNNBlock(input_size, channels[0], kernel_sizes[0], dilations[0]))
         for i in range(1, len(channels) - 1):
@@ -144,7 +144,32 @@ class EcapaTdnn(NativeBackbone):
             cfg.channels[i], cfg.kernel_sizes[i], cfg.dilations[i] = self.channels[i], self.kernel_sizes[i], self.dilations[i]
         cfg.attention_channels, cfg.res2net_scale, cfg.se_channels = self.attention_channels, self.res2net_scale, self.se_channels
         cfg.pooling = self._POOLING[self.pooling_type]
+        cfg.global_context = 1 if self.global_context else 0
         return _lib.PPV_MODEL_ECAPA_TDNN, cfg
+
+    def forward(self, x, lengths=None):
+        """reference: ecapa_tdnn.py:245-276.  x [N, time, freq] float32 CUDA -> [N, embd_dim].  ``lengths`` [N]: relative lengths in
+        (0, 1]; SEBlock and ASP then use the first #{t : t < lengths * T} frames only (ecapa_tdnn.py:71-75, pooling.py:96-115)."""
+        if lengths is None:
+            return super().forward(x)
+        if self.pooling_type != "ASP":  # pooling.py:17,39,60: the other pooling layers accept and ignore `lengths`; SEBlock does not
+            raise NotImplementedError('lengths with pooling_type != "ASP" is not implemented on B200')
+        if self.training:
+            raise _lib.PPVError('EcapaTdnn on B200 implements the eval-mode forward only; call .eval()')
+        _lib.require_cuda(x, 'x')
+        x = x.to(torch.float32).contiguous()
+        B, T, F = x.shape
+        assert F == self.input_size
+        lengths = torch.as_tensor(lengths, dtype=torch.float32, device=x.device).contiguous()
+        assert lengths.shape == (B,)
+        with torch.cuda.device(x.device):
+            h = self._get_handle()
+            ws = self._workspace(B, T, x.device)
+            emb = torch.empty((B, self.embd_dim), dtype=torch.float32, device=x.device)
+            _lib.check(_lib.load().ppv_model_forward_lengths(h, _lib.ptr(x), _lib.ptr(lengths), B, T, _lib.ptr(emb),
+                                                              C.c_void_p(ws.data_ptr()), ws.numel(), _lib.current_stream()),
+                       'ppv_model_forward_lengths')
+        return emb
 
     def forward_wav(self, featurizer, waveforms, input_lens_ratio=None):
         """Fused waveform -> embedding path (``ppv_model_forward_wav``): equals

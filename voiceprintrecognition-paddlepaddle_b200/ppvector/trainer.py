@@ -5,7 +5,9 @@ return values; featurisation, the backbone and the trial x enrol cosine matrix r
 minDCF stay host numpy.  ``train`` (trainer.py:281-365 with the step of :206-229) runs the CUDA training step of
 ``ppvector.train_engine.TrainEngine`` (train-mode forward, AAM loss, backward, one gradient all-reduce over NCCL, Adam) with the
 reference's schedules; it is implemented for EcapaTdnn + AAMLoss + Adam + WarmupCosineSchedulerLR (configs/ecapa_tdnn.yml) and
-raises for other combinations.  VisualDL logging and checkpoint rotation are out of scope: the weights are saved with torch."""
+raises for other combinations.  Checkpoints follow the reference's directory layout (``<model>_<feature>/{epoch_N,last_model,best_model}``
+with best-EER tracking, optimizer state and ``model.state``) and ``resume_model`` / an existing ``last_model`` restore the weights, the Adam
+moments, the step counters of both schedules and the epoch.  VisualDL logging is out of scope."""
 import os
 
 import numpy as np
@@ -21,7 +23,7 @@ from ppvector.data_utils.reader import PPVectorDataset
 from ppvector.metric.cosine import cosine_matrix
 from ppvector.metric.metrics import compute_dcf, compute_eer, compute_fnr_fpr
 from ppvector.models import build_model
-from ppvector.utils.checkpoint import load_state_dict_file
+from ppvector.utils.checkpoint import find_resume_dir, load_checkpoint_dir, load_state_dict_file, save_checkpoint
 from ppvector.utils.utils import dict_to_object, print_arguments
 
 
@@ -140,8 +142,8 @@ class PPVectorTrainer(object):
 
     def train(self, save_model_path='models/', log_dir='log/', resume_model=None, pretrained_model=None, do_eval=True, max_steps=None):
         """reference: trainer.py:281-365.  ``max_steps`` (extension) stops early -- used by the tests and the bench tool.
-        ``pretrained_model`` / ``resume_model`` restore the weights (backbone and classifier); the optimizer moments and the
-        epoch counter of a reference checkpoint (optimizer.pdopt / model.state) are not restored: training restarts its schedules."""
+        ``pretrained_model`` restores weights only (checkpoint.py:11-42); ``resume_model`` -- or ``<save_model_path>/<model>_<feature>/
+        last_model`` when it exists -- restores weights, Adam moments and step count, both schedules and the epoch (checkpoint.py:45-101)."""
         import random as _random
 
         import torch.distributed as dist
@@ -173,20 +175,42 @@ class PPVectorTrainer(object):
         num_speakers = int(cf.model_conf.classifier.num_speakers)
         model_args = dict(cf.model_conf.get('model_args', {}))
         backbone = build_model(input_size=fz.feature_dim, configs=cf)  # random init with the mirror's initialisers, names = state_dict
-        engine = TrainEngine(input_size=fz.feature_dim, num_speakers=num_speakers, embd_dim=model_args.get('embd_dim', 192), device=self.device)
+        cls_conf = dict(cf.model_conf.get('classifier', {}))
+        if model_args.get('pooling_type', 'ASP') != 'ASP' or not model_args.get('global_context', True):
+            raise NotImplementedError('the B200 training step implements pooling_type="ASP" with global_context')
+        if cls_conf.get('classifier_type', 'Cosine') != 'Cosine' or int(cls_conf.get('K', 1)) != 1 or int(cls_conf.get('num_blocks', 0)) != 0:
+            raise NotImplementedError('the B200 training step implements classifier_type="Cosine", K=1, num_blocks=0')
+        engine_args = {k: model_args[k] for k in ('channels', 'kernel_sizes', 'dilations', 'attention_channels', 'res2net_scale', 'se_channels')
+                       if k in model_args}
+        engine = TrainEngine(input_size=fz.feature_dim, num_speakers=num_speakers, embd_dim=model_args.get('embd_dim', 192), device=self.device,
+                             **engine_args)
         shapes = {k: tuple(v.shape) for k, v in backbone.state_dict().items()}
         sd = {k: v for k, v in backbone.state_dict().items()}
         cls_w = torch.empty(engine.embd_dim, num_speakers)
         torch.nn.init.xavier_uniform_(cls_w)  # fc.py:34-36
-        for path in (pretrained_model, resume_model):
-            if path is not None:
+        resume_dir = find_resume_dir(cf, save_model_path, resume_model)
+        opt_state, run_state = None, {}
+        for path, is_resume in ((pretrained_model, False), (resume_dir, True)):
+            if path is None:
+                continue
+            if is_resume:
+                loaded, opt_state, run_state = load_checkpoint_dir(path)
+            else:
                 loaded = load_state_dict_file(path)
-                for k, v in loaded.items():
-                    if k.startswith('1.') or k == 'classifier.weight':
-                        cls_w = torch.as_tensor(np.asarray(v))
-                    else:
-                        sd[k[2:] if k.startswith('0.') else k] = torch.as_tensor(np.asarray(v))
+            for k, v in loaded.items():
+                if k.startswith('1.') or k == 'classifier.weight':
+                    cls_w = torch.as_tensor(np.asarray(v))
+                else:
+                    sd[k[2:] if k.startswith('0.') else k] = torch.as_tensor(np.asarray(v))
         engine.load_state_dict(sd, cls_w)
+        last_epoch, best_eer = 0, 1.0
+        if opt_state is not None:  # checkpoint.py:64-85: optimizer state, epoch counter, best EER
+            engine.exp_avg.copy_(opt_state['exp_avg'])
+            engine.exp_avg_sq.copy_(opt_state['exp_avg_sq'])
+            engine.step_count = int(opt_state['step_count'])
+            last_epoch = int(run_state.get('last_epoch', opt_state.get('last_epoch', 0)))
+            best_eer = float(run_state.get('eer', 1.0))
+            logger.info(f'成功恢复模型参数和优化方法参数：{resume_dir}')
         if world > 1:  # every rank starts from rank 0's weights (fleet.distributed_model broadcasts them)
             dist.broadcast(engine.params, src=0)
             dist.broadcast(engine.stats, src=0)
@@ -195,14 +219,34 @@ class PPVectorTrainer(object):
         loss_args = dict(cf.loss_conf.get('loss_args', {}))
         criterion = AAMLoss(**loss_args)
         margin_scheduler = None
-        if cf.loss_conf.get('use_margin_scheduler', False):
-            margin_scheduler = MarginScheduler(criterion=criterion, step_per_epoch=steps_per_epoch, increase_start_epoch=int(cf.train_conf.max_epoch * 0.3),
-                                               fix_epoch=int(cf.train_conf.max_epoch * 0.7), **dict(cf.loss_conf.get('margin_scheduler_args', {})))
+        if cf.loss_conf.get('use_margin_scheduler', False):  # trainer.py:182-190: defaults overridden with dict.update
+            ms_args = dict(increase_start_epoch=int(cf.train_conf.max_epoch * 0.3), fix_epoch=int(cf.train_conf.max_epoch * 0.7))
+            ms_args.update(dict(cf.loss_conf.get('margin_scheduler_args', {}) or {}))
+            margin_scheduler = MarginScheduler(criterion=criterion, step_per_epoch=steps_per_epoch, **ms_args)
+        if last_epoch > 0:  # checkpoint.py:80-84: replay the schedules up to the resumed epoch
+            for _ in range(last_epoch * steps_per_epoch):
+                scheduler.step()
+            if margin_scheduler is not None:
+                margin_scheduler.step(current_step=last_epoch * steps_per_epoch)
         wd = float(dict(cf.optimizer_conf.get('optimizer_args', {})).get('weight_decay', 0.0))
         logger.info('训练数据：{}'.format(len(train_dataset)))
-        self.train_step, self.train_loss, self.train_acc = 0, None, None
+        self.train_step, self.train_loss, self.train_acc = last_epoch * steps_per_epoch, None, None
+        self.eval_eer = self.eval_min_dcf = self.eval_threshold = None
         history = []
-        for epoch_id in range(int(cf.train_conf.max_epoch)):
+
+        def checkpoint(epoch_no, best):
+            self._state_dict = {k: v.cpu().numpy() for k, v in engine.state_dict(shapes).items()}
+            # keys as in the reference's Sequential(backbone, classifier) checkpoint: "0.<backbone tensor>", "1.weight"
+            ckpt = {'0.' + k: torch.from_numpy(v) for k, v in self._state_dict.items()}
+            ckpt['1.weight'] = engine.view('classifier.weight', (engine.embd_dim, num_speakers)).detach().cpu().clone()
+            opt = {'exp_avg': engine.exp_avg.detach().cpu(), 'exp_avg_sq': engine.exp_avg_sq.detach().cpu(), 'step_count': engine.step_count,
+                   'last_epoch': epoch_no, 'scheduler_last_epoch': getattr(scheduler, 'last_epoch', None),
+                   'margin_step': getattr(margin_scheduler, 'current_step', None)}
+            return save_checkpoint(cf, ckpt, opt, save_model_path, epoch_no, eer=self.eval_eer, min_dcf=self.eval_min_dcf,
+                                   threshold=self.eval_threshold, margin=margin_scheduler.get_margin() if margin_scheduler else None,
+                                   best_model=best)
+
+        for epoch_id in range(last_epoch, int(cf.train_conf.max_epoch)):
             losses, accs = [], []
             for features, label, _lens in self._train_batches(train_dataset, batch_size, epoch_id, rank, world, sampler.get('shuffle', True),
                                                               sampler.get('drop_last', True)):
@@ -228,17 +272,17 @@ class PPVectorTrainer(object):
                 break
             if world > 1:
                 dist.barrier()  # the reference lets rank 0 evaluate while the others run ahead; keep the ranks together
-            if rank == 0:
+            if rank == 0:  # trainer.py:336-365: evaluate, keep the best-EER model, save epoch_N / last_model
+                epoch_no = epoch_id + 1
                 self._state_dict = {k: v.cpu().numpy() for k, v in engine.state_dict(shapes).items()}
-                os.makedirs(save_model_path, exist_ok=True)
-                # keys as in the reference's Sequential(backbone, classifier) checkpoint: "0.<backbone tensor>", "1.weight"
-                ckpt = {'0.' + k: torch.from_numpy(v) for k, v in self._state_dict.items()}
-                ckpt['1.weight'] = engine.view('classifier.weight', (engine.embd_dim, num_speakers)).detach().cpu().clone()
-                torch.save(ckpt, os.path.join(save_model_path, 'model.pt'))
                 if do_eval and os.path.exists(cf.dataset_conf.enroll_list):
                     self.model = None
-                    eer, min_dcf, threshold = self.evaluate()
-                    logger.info(f'Test epoch: {epoch_id}, threshold: {threshold:.2f}, EER: {eer:.5f}, MinDCF: {min_dcf:.5f}')
+                    self.eval_eer, self.eval_min_dcf, self.eval_threshold = self.evaluate()
+                    logger.info(f'Test epoch: {epoch_no}, threshold: {self.eval_threshold:.2f}, EER: {self.eval_eer:.5f}, MinDCF: {self.eval_min_dcf:.5f}')
+                    if self.eval_eer <= best_eer:
+                        best_eer = self.eval_eer
+                        checkpoint(epoch_no, best=True)
+                checkpoint(epoch_no, best=False)
         self._state_dict = {k: v.cpu().numpy() for k, v in engine.state_dict(shapes).items()}
         self.engine = engine
         return history
