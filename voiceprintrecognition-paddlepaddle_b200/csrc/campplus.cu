@@ -20,6 +20,8 @@
 //   linear_local * mask     3-tap gather-GEMM whose epilogue multiplies by the mask of (utterance, segment)
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "common.h"
 #include "model_common.h"
 #include "ptx.cuh"
@@ -54,8 +56,9 @@ struct TransitW {
 };
 
 struct CStep {
-    enum Kind { STEM, GEMM, ADD_RELU, FLATTEN, BN_RELU, CONTEXT, STATS } kind;
+    enum Kind { STEM, GEMM, CONV3, ADD_RELU, FLATTEN, BN_RELU, CONTEXT, STATS } kind;
     GemmParams gp;
+    Conv3x3Params c3;  // CONV3: the 32 -> 32 channel 3x3 convs of the FCM head (conv3x3.cu)
     int BN = 0;
     Planes a, b, d;
     const float *p0 = nullptr, *p1 = nullptr, *p2 = nullptr, *p3 = nullptr, *p4 = nullptr, *p5 = nullptr;
@@ -541,6 +544,23 @@ static int cp_build_plan(CamppModel* m, int B, int T, void* ws, size_t ws_bytes,
         for (int dh = -1; dh <= 1; ++dh)
             for (int dw = -1; dw <= 1; ++dw) v->push_back(GemmSource{p, 0, 32, dh * g.Wp + dw});
     };
+    const char* c3env = getenv("PPV_CONV3X3");  // 0 = run the 3x3 convs through the generic gather-GEMM (debugging / A-B timing)
+    const bool use_c3 = !(c3env && c3env[0] == '0');
+    // 3x3 conv, 32 -> 32 channels, on grid `g` of buffer `p`: the patch kernel (conv3x3.cu), else nine taps of the gather-GEMM
+    auto add_conv3 = [&](const GemmWeights& gw, const Planes& p, const ImageGeo& g, Epilogue ep) -> int {
+        if (use_c3 && gw.N == 32 && conv3x3_c32_supported(32, gw.N, g.H, g.W)) {
+            ep.bias = gw.bias;
+            CStep s;
+            s.kind = CStep::CONV3;
+            int rc = conv3x3_build(&s.c3, p, 0, gw.W, B, g.H, g.W, g.Hp, g.Wp, ep);
+            if (rc) return rc;
+            m->steps.push_back(s);
+            return PPV_OK;
+        }
+        std::vector<GemmSource> t;
+        taps9(p, g, &t);
+        return add_gemm(gw, t, int(g.rows(B)), ep);
+    };
     auto relu = [](Epilogue ep) {
         ep.relu = 1;
         return ep;
@@ -557,12 +577,9 @@ static int cp_build_plan(CamppModel* m, int B, int T, void* ws, size_t ws_bytes,
         const ResBlockW& rw = m->res[i];
         const ImageGeo& gin = m->geo[rw.stride == 2 ? rw.stage - 1 : rw.stage];
         const ImageGeo& go = m->geo[rw.stage];
-        std::vector<GemmSource> t1, t2;
-        taps9(x, gin, &t1);
-        rc = add_gemm(rw.conv1, t1, int(gin.rows(B)), relu(img_epi(cb.c1[i], gin, go, rw.stride)));
+        rc = add_conv3(rw.conv1, x, gin, relu(img_epi(cb.c1[i], gin, go, rw.stride)));
         if (rc) return rc;
-        taps9(cb.c1[i], go, &t2);
-        rc = add_gemm(rw.conv2, t2, int(go.rows(B)), img_epi(cb.c2[i], go, go, 1));
+        rc = add_conv3(rw.conv2, cb.c1[i], go, img_epi(cb.c2[i], go, go, 1));
         if (rc) return rc;
         Planes resid = x;
         if (rw.has_sc) {
@@ -583,9 +600,7 @@ static int cp_build_plan(CamppModel* m, int B, int T, void* ws, size_t ws_bytes,
         m->stage_out[rw.stage] = x;
     }
     {
-        std::vector<GemmSource> t;
-        taps9(x, m->geo[2], &t);
-        rc = add_gemm(m->head_conv2, t, int(m->geo[2].rows(B)), relu(img_epi(cb.head_out, m->geo[2], m->geo[3], 2)));
+        rc = add_conv3(m->head_conv2, x, m->geo[2], relu(img_epi(cb.head_out, m->geo[2], m->geo[3], 2)));
         if (rc) return rc;
         CStep s;
         s.kind = CStep::FLATTEN;
@@ -697,6 +712,7 @@ int campplus_forward(CamppModel* m, const float* feat, int B, int T, float* emb,
                 rc = launch_stem_conv(feat, B, T, m->cfg.input_size, m->stem_w, m->stem_b, 32, m->stem_out, m->geo[0].Hp, m->geo[0].Wp, st);
                 break;
             case CStep::GEMM: rc = gemm_launch(s.gp, s.BN, m->precision, m->num_sms, st); break;
+            case CStep::CONV3: rc = conv3x3_launch(s.c3, m->precision, m->num_sms, st); break;
             case CStep::ADD_RELU: rc = launch_se_scale_res(s.a, nullptr, s.b, 0, s.d, 0, s.C, s.img_rows, s.rows, m->num_sms, st, 1, 0.f); break;
             case CStep::FLATTEN: {
                 const ImageGeo& g = m->geo[3];

@@ -171,6 +171,19 @@ struct Res2Params {
 int res2conv_build(Res2Params* rp, const GemmSource* srcs, int nsrc, const Planes& W, int M, int dil, const Epilogue& epi);
 int res2conv_launch(const Res2Params& rp, int precision, int num_sms, cudaStream_t st);
 
+// ---- 3x3 conv, 32 -> 32 channels, over zero-bordered image grids: weight-stationary, one image patch per work item (conv3x3.cu) ----
+struct Conv3x3Params {
+    CUtensorMap mapX;  // 5-D {C, Wp, Hp, B, plane}, box {32, 64, 8, 1, 1}, SWIZZLE_64B
+    CUtensorMap mapW;  // weight planes [2][>= 32][9 x 32], box {32, 32, 1}, SWIZZLE_64B
+    int x_col0;
+    int B, H, W, Hp, Wp;
+    int nph, npw, patches;
+    Epilogue epi;
+};
+bool conv3x3_c32_supported(int Cin, int Cout, int H, int W);
+int conv3x3_build(Conv3x3Params* cp, const Planes& x, int x_col0, const Planes& Wt, int B, int H, int W, int Hp, int Wp, const Epilogue& epi);
+int conv3x3_launch(const Conv3x3Params& cp, int precision, int num_sms, cudaStream_t st);
+
 // ---- the whole Res2Net chain of a block, one utterance per CTA, operands resident in shared memory (res2chain.cu) ----------
 constexpr int RES2CHAIN_MAX = 7;
 struct Res2ChainParams {

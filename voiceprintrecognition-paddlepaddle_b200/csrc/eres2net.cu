@@ -15,6 +15,8 @@
 //   * TSTP = column mean and sqrt(unbiased variance + 1e-8) over time of the flattened [B, T', 512*F'] matrix.
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "common.h"
 #include "model_common.h"
 
@@ -36,7 +38,8 @@ struct EFuseW {  // layerN_downsample + fuse_modeXYZ
 };
 
 struct EStep {
-    enum Kind { STEM, GEMM, ADD_RELU, AFF_COMBINE, FLATTEN, TSTP } kind;
+    enum Kind { STEM, GEMM, CONV3, ADD_RELU, AFF_COMBINE, FLATTEN, TSTP } kind;
+    Conv3x3Params c3;  // CONV3: single-source 3x3 conv over a 32-channel (padded) chunk, conv3x3.cu
     GemmParams gp;
     int BN = 0;
     Planes a, b, c, d;
@@ -398,6 +401,8 @@ static int er_build_plan(ERes2NetModel* m, int B, int T, void* ws, size_t ws_byt
     Planes x = eb.stem_out;
     Planes stage_out[5];
     int rc;
+    const char* c3env = getenv("PPV_CONV3X3");  // 0 = 3x3 convs through the generic gather-GEMM (debugging / A-B timing)
+    const bool use_c3 = !(c3env && c3env[0] == '0');
     for (size_t i = 0; i < m->blocks.size(); ++i) {
         const EBlockW& bw = m->blocks[i];
         const ImageGeo& gin = m->geo[bw.stride == 2 ? bw.stage - 1 : bw.stage];
@@ -407,10 +412,20 @@ static int er_build_plan(ERes2NetModel* m, int B, int T, void* ws, size_t ws_byt
         rc = add_gemm(bw.conv1, {GemmSource{x, 0, bw.in_planes, 0}}, Min, relu20(img_epi(eb.c1[i], gin, go, bw.stride)));
         if (rc) return rc;
         // first 3x3 on chunk 0
-        std::vector<GemmSource> ta;
-        taps9(eb.c1[i], 0, wp, go, &ta);
-        rc = add_gemm(bw.conv_a, ta, Mo, relu20(img_epi(eb.s0[i], go, go, 1)));
-        if (rc) return rc;
+        if (use_c3 && wp == 32 && bw.conv_a.N == 32 && bw.conv_a.Ktot == 9 * 32) {  // weight-stationary patch kernel (conv3x3.cu)
+            Epilogue ep = relu20(img_epi(eb.s0[i], go, go, 1));
+            ep.bias = bw.conv_a.bias;
+            EStep s3;
+            s3.kind = EStep::CONV3;
+            rc = conv3x3_build(&s3.c3, eb.c1[i], 0, bw.conv_a.W, B, go.H, go.W, go.Hp, go.Wp, ep);
+            if (rc) return rc;
+            m->steps.push_back(s3);
+        } else {
+            std::vector<GemmSource> ta;
+            taps9(eb.c1[i], 0, wp, go, &ta);
+            rc = add_gemm(bw.conv_a, ta, Mo, relu20(img_epi(eb.s0[i], go, go, 1)));
+            if (rc) return rc;
+        }
         // second 3x3
         std::vector<GemmSource> tb;
         if (!bw.fuse) {
@@ -507,6 +522,7 @@ int eres2net_forward(ERes2NetModel* m, const float* feat, int B, int T, float* e
                 rc = launch_stem_conv(feat, B, T, m->cfg.input_size, m->stem_w, m->stem_b, m->cfg.m_channels, m->stem_out, m->geo[1].Hp, m->geo[1].Wp, st);
                 break;
             case EStep::GEMM: rc = gemm_launch(s.gp, s.BN, m->precision, m->num_sms, st); break;
+            case EStep::CONV3: rc = conv3x3_launch(s.c3, m->precision, m->num_sms, st); break;
             case EStep::ADD_RELU:
                 rc = launch_se_scale_res(s.a, nullptr, s.b, 0, s.d, 0, s.C, s.img_rows, s.rows, m->num_sms, st, 1, ER_RELU_MAX);
                 break;

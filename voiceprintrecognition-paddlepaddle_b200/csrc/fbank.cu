@@ -31,6 +31,7 @@ constexpr int FB_SCR = 17 * 16;       // float2 scratch per frame: [k1][n2] padd
 constexpr int FB_MAX_MELS = 128;
 constexpr int FB_PART_ROWS = 32768;   // handle-owned partial-sum rows ([row][FB_MAX_MELS]): utterances x items per launch group
 constexpr int FB_FIN_FRAMES = 32;     // frames per finalize block
+constexpr int FB_TW512 = 144;         // e^{-2 pi i k / 512} is needed for k <= 143 only (bins k and 256 - k share a pair)
 
 struct FbankTables {
     float* window = nullptr;    // [512] zero-padded
@@ -112,7 +113,7 @@ __host__ __device__ inline FbankSmem fbank_smem_layout(int nnz, int n_mels, int 
     int o = 0;
     auto take = [&](int bytes) { const int at = o; o += (bytes + 15) & ~15; return at; };
     L.tw = take(256 * 8);
-    L.tw512 = take(256 * 8);
+    L.tw512 = take(FB_TW512 * 8);
     L.win = take(FB_NFFT * 4);
     L.melw = take(nnz * 4);
     L.mstart = take(n_mels * 4);
@@ -152,10 +153,8 @@ __global__ void __launch_bounds__(FB_THREADS, 3)
     const int nitem = (T + FB_ITEM - 1) / FB_ITEM;
     const int total = B * nitem;
 
-    for (int i = tid; i < 256; i += FB_THREADS) {
-        s_tw[i] = tb.tw[i];
-        s_tw512[i] = tb.tw512[i];
-    }
+    for (int i = tid; i < 256; i += FB_THREADS) s_tw[i] = tb.tw[i];
+    for (int i = tid; i < FB_TW512; i += FB_THREADS) s_tw512[i] = tb.tw512[i];
     for (int i = tid; i < FB_NFFT; i += FB_THREADS) s_win[i] = tb.window[i];
     for (int i = tid; i < tb.nnz; i += FB_THREADS) s_melw[i] = tb.mel_w[i];
     for (int i = tid; i < n_mels; i += FB_THREADS) {
@@ -532,6 +531,7 @@ int fbank_run(Fbank* h, const float* wav, const float* lens_ratio, int B, int L,
     const int F = h->cfg.n_mels;
     const FbankSmem lay = fbank_smem_layout(h->tb.nnz, F, h->win, h->shift);
     PPV_REQUIRE(lay.total <= 200 * 1024, "fbank_run: shared memory budget exceeded (frame shift too large)");
+    // three CTAs per SM need <= 76 800 B each (228 KB - 1 KB reserved per CTA): 76 272 B for 16 kHz / 25 ms / 10 ms / 80 bins
     const bool vec = (h->shift % 2) == 0;
     auto kern = (h->win == 400) ? (vec ? fbank_logmel_kernel<true, 400> : fbank_logmel_kernel<false, 400>)
                                 : (vec ? fbank_logmel_kernel<true, 0> : fbank_logmel_kernel<false, 0>);

@@ -89,11 +89,13 @@ __device__ __forceinline__ void epilogue_math(const Epilogue& ep, int N, int col
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const Epilogue& ep, const CUtensorMap* map_out, int M, int N, int m0, int n0,
                                               uint32_t tmem_acc, uint32_t tfull_bar, uint32_t acc_phase, uint32_t tempty_bar, int q,
-                                              int lane, int ehalf, int etid, uint32_t staging, uint8_t* staging_gen, int64_t out_row_shift = 0) {
+                                              int lane, int ehalf, int etid, uint32_t staging, uint8_t* staging_gen, int64_t out_row_shift = 0,
+                                              int64_t row_override = INT64_MIN) {
     // row bookkeeping
     const int rloc = q * 32 + lane;  // row within the tile == TMEM lane
-    const int64_t row = int64_t(m0) + rloc;
-    bool valid = row < M;
+    // row_override (conv3x3.cu): the caller maps this accumulator lane to its GEMM row itself (-1: the lane holds no output)
+    const int64_t row = row_override == INT64_MIN ? int64_t(m0) + rloc : (row_override < 0 ? 0 : row_override);
+    bool valid = row_override == INT64_MIN ? row < M : row_override >= 0;
     int64_t mirror_a = -1, mirror_b = -1;
     int64_t grp = 0, sgrp = 0;
     int64_t out_row = row + out_row_shift;  // wgrad mode: partial block of this K split

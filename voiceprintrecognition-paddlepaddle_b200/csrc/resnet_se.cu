@@ -34,7 +34,8 @@ struct BlockW {
 };
 
 struct RStep {
-    enum Kind { CONV1, GEMM, POOL, SCALE_RES, FLATTEN, ASP_GLOBAL, ASP_FUSED } kind;
+    enum Kind { CONV1, GEMM, CONV3, POOL, SCALE_RES, FLATTEN, ASP_GLOBAL, ASP_FUSED } kind;
+    Conv3x3Params c3;  // CONV3: 3x3 conv with 32 -> 32 channels (layer1), conv3x3.cu
     GemmParams gp;
     AspFusedParams ap;
     int BN = 0;
@@ -399,16 +400,33 @@ void rs_carve(const ResNetSEModel* m, WsCarver& cv, int B, int T, Geo* geo, RsBu
     rb->res.resize(nb);
     rb->blk_out.resize(nb);
     int maxC = 0;
+    // Buffer liveness (round 2; every buffer used to be dedicated: 38 GB at batch 256).  One set of image buffers per STAGE: conv1 / conv2 /
+    // conv3 outputs are dead once the block's SE pass has run, and the block output overwrites its own residual input in place
+    // (out = s * z + res is elementwise).  The first block of a stage runs conv1 on the PREVIOUS stage's grid: that output aliases
+    // the previous stage's conv3 buffer (same grid, same channel count, dead by then).  Zero borders survive because epilogues only
+    // ever store interior positions and a buffer never changes its grid.
+    Planes s_out1[5], s_out2[5], s_out3[5], s_act[5];
     for (size_t i = 0; i < nb; ++i) {
         const BlockW& bw = m->blocks[i];
-        const Geo& gin = geo[bw.stride == 2 ? bw.stage - 1 : bw.stage];
-        const Geo& gout = geo[bw.stage];
-        // every image buffer is dedicated: its zero border is written once (memset) and never again
-        rb->out1[i] = cv.planes(gin.rows(B), bw.planes);
-        rb->out2[i] = cv.planes(gout.rows(B), bw.planes);
-        rb->out3[i] = cv.planes(gout.rows(B), 2 * bw.planes);
-        if (bw.has_down) rb->res[i] = cv.planes(gout.rows(B), 2 * bw.planes);
-        rb->blk_out[i] = cv.planes(gout.rows(B), 2 * bw.planes);
+        const int st = bw.stage;
+        const Geo& gin = geo[bw.stride == 2 ? st - 1 : st];
+        const Geo& gout = geo[st];
+        if (!s_act[st].base && s_act[st].rows == 0) {  // first block of the stage: carve the stage's set
+            s_out1[st] = cv.planes(gout.rows(B), bw.planes);
+            s_out2[st] = cv.planes(gout.rows(B), bw.planes);
+            s_out3[st] = cv.planes(gout.rows(B), 2 * bw.planes);
+            s_act[st] = cv.planes(gout.rows(B), 2 * bw.planes);
+        }
+        if (bw.stride == 2) {
+            const bool can_alias = st > 1 && s_out3[st - 1].rows > 0 && s_out3[st - 1].ld == bw.planes;
+            rb->out1[i] = can_alias ? s_out3[st - 1] : cv.planes(gin.rows(B), bw.planes);
+        } else {
+            rb->out1[i] = s_out1[st];
+        }
+        rb->out2[i] = s_out2[st];
+        rb->out3[i] = s_out3[st];
+        if (bw.has_down) rb->res[i] = s_act[st];
+        rb->blk_out[i] = s_act[st];
         maxC = std::max(maxC, 2 * bw.planes);
     }
     const int Tf = geo[4].W;
@@ -496,6 +514,8 @@ static int rs_build_plan(ResNetSEModel* m, int B, int T, void* ws, size_t ws_byt
     }
     Planes x = rb.conv1_out;
     int rc;
+    const char* c3env = getenv("PPV_CONV3X3");  // 0 = 3x3 convs through the generic gather-GEMM (debugging / A-B timing)
+    const bool use_c3 = !(c3env && c3env[0] == '0');
     for (size_t i = 0; i < m->blocks.size(); ++i) {
         const BlockW& bw = m->blocks[i];
         const Geo& gin = m->geo[bw.stride == 2 ? bw.stage - 1 : bw.stage];
@@ -505,11 +525,21 @@ static int rs_build_plan(ResNetSEModel* m, int B, int T, void* ws, size_t ws_byt
         rc = add_gemm(bw.conv1, {GemmSource{x, 0, bw.inplanes, 0}}, Min, img_epi(rb.out1[i], gin, gin, 1, true), std::max(p, 32));
         if (rc) return rc;
         // conv2 3x3 (stride) + BN + ReLU: 9 taps on the input grid, stored on the output grid
-        std::vector<GemmSource> taps;
-        for (int dh = -1; dh <= 1; ++dh)
-            for (int dw = -1; dw <= 1; ++dw) taps.push_back(GemmSource{rb.out1[i], 0, p, dh * gin.Wp + dw});
-        rc = add_gemm(bw.conv2, taps, Min, img_epi(rb.out2[i], gin, gout, bw.stride, true), std::max(p, 32));
-        if (rc) return rc;
+        if (use_c3 && p == 32 && conv3x3_c32_supported(p, p, gin.H, gin.W)) {  // weight-stationary patch kernel (conv3x3.cu)
+            Epilogue ep = img_epi(rb.out2[i], gin, gout, bw.stride, true);
+            ep.bias = bw.conv2.bias;
+            RStep s3;
+            s3.kind = RStep::CONV3;
+            rc = conv3x3_build(&s3.c3, rb.out1[i], 0, bw.conv2.W, B, gin.H, gin.W, gin.Hp, gin.Wp, ep);
+            if (rc) return rc;
+            m->steps.push_back(s3);
+        } else {
+            std::vector<GemmSource> taps;
+            for (int dh = -1; dh <= 1; ++dh)
+                for (int dw = -1; dw <= 1; ++dw) taps.push_back(GemmSource{rb.out1[i], 0, p, dh * gin.Wp + dw});
+            rc = add_gemm(bw.conv2, taps, Min, img_epi(rb.out2[i], gin, gout, bw.stride, true), std::max(p, 32));
+            if (rc) return rc;
+        }
         // conv3 1x1 + BN
         rc = add_gemm(bw.conv3, {GemmSource{rb.out2[i], 0, p, 0}}, Mout, img_epi(rb.out3[i], gout, gout, 1, false), C);
         if (rc) return rc;
@@ -650,6 +680,7 @@ int resnetse_forward(ResNetSEModel* m, const float* feat, int B, int T, float* e
                 break;
             }
             case RStep::GEMM: rc = gemm_launch(s.gp, s.BN, m->precision, m->num_sms, st); break;
+            case RStep::CONV3: rc = conv3x3_launch(s.c3, m->precision, m->num_sms, st); break;
             case RStep::POOL:
                 rc = launch_colstats(s.a, 0, s.C, B, s.img_rows, 0, s.img_rows, 0, 0.f, nullptr, s.b, st, s.inv_count);
                 break;

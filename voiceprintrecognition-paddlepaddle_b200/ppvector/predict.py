@@ -157,8 +157,9 @@ class PPVectorPredictor:
         return self.extract_embeddings(seg.samples[None, :])[0]
 
     def predict_batch(self, audios_data, sample_rate=16000, batch_size=32):
-        """reference: predict.py:235-269.  Zero-pad to the longest, lens ratio mask after CMN (featurizer.py:48-59);
-        ``batch_size`` is accepted for signature compatibility (the whole batch is one launch sequence)."""
+        """reference: predict.py:235-269.  Zero-pad to the longest of the WHOLE list, lens-ratio mask after CMN (featurizer.py:48-59),
+        then the model in chunks of ``batch_size`` (predict.py:264-267).  Featurisation is per utterance, so chunking the padded
+        waveforms gives the same embeddings as featurising the whole list at once, and bounds the workspace."""
         segs = [self._load_audio(audio_data=a, sample_rate=sample_rate).samples for a in audios_data]
         max_len = max(s.shape[0] for s in segs)
         inputs = np.zeros((len(segs), max_len), dtype=np.float32)
@@ -166,7 +167,9 @@ class PPVectorPredictor:
         for i, s in enumerate(segs):
             inputs[i, :s.shape[0]] = s
             ratio[i] = s.shape[0] / max_len
-        return self.extract_embeddings(inputs, ratio)
+        batch_size = max(1, int(batch_size))
+        return np.concatenate([self.extract_embeddings(inputs[i:i + batch_size], ratio[i:i + batch_size])
+                               for i in range(0, len(segs), batch_size)], axis=0)
 
     def contrast(self, audio_data1, audio_data2):
         """reference: predict.py:271-283 -> cosine similarity of the two embeddings"""
