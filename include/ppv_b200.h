@@ -67,6 +67,10 @@ void ppv_fbank_default_cfg(ppv_fbank_cfg* cfg);
 int ppv_fbank_create(const ppv_fbank_cfg* cfg, ppv_fbank_t** out);
 int ppv_fbank_destroy(ppv_fbank_t* h);
 /* snip_edges frame count for L samples (0 if L < window). */
+/* As ppv_fbank_forward for a zero-padded batch of utterances of DIFFERENT lengths, each featurised as if alone (the training data
+ * path, reader.py:101-104 + collate_fn.py:5-23): valid_frames[b] (device int32) frames of utterance b are real; the time mean is taken
+ * over those only and frames beyond them are written as zeros. */
+int ppv_fbank_forward_ragged(ppv_fbank_t* h, const float* wav, const int32_t* valid_frames, int B, int L, float* out, void* stream);
 int ppv_fbank_num_frames(const ppv_fbank_t* h, int L);
 int ppv_fbank_feature_dim(const ppv_fbank_t* h);
 /* wav [B,L] fp32 in [-1,1] -> out [B,T,n_mels] fp32, time-mean subtracted; if lens_ratio != NULL,
@@ -257,6 +261,36 @@ int ppv_cosine_matrix(const float* A, const float* Bm, int M, int N, int D, floa
                       void* stream);
 /* E [n,D], idx [P,2] int32 -> out [P]. */
 int ppv_cosine_pairlist(const float* E, const int32_t* idx, int64_t P, int n, int D, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Batched waveform preparation / augmentation in front of the feature extractor.  Replaces the per-utterance CPU work of
+ * ppvector/data_utils/reader.py:85-104, :153-163 (yeaudio: change_speed, gain_db, add noise at an SNR, normalize(target_db), crop)
+ * with one launch sequence per batch; the random draws stay on the host (configs/augmentation.yml).
+ * Per utterance b: iparams[b] = {raw_len, new_len (= int(raw_len / speed), or raw_len), crop_start, crop_len, noise_off, noise_len,
+ * has_noise, 0}; fparams[b] = {reserved, volume gain dB, SNR dB, 0}.  wav [B][wav_ld] fp32, noise = concatenated noise clips (tiled
+ * over the utterance from noise_off), out [B][Lout] fp32 zero-padded.  normalize != 0: dB-normalise to target_db over the whole
+ * augmented utterance before the crop.
+ * ------------------------------------------------------------------------------------------- */
+#define PPV_PREP_NI 8
+#define PPV_PREP_NF 4
+size_t ppv_audio_prep_workspace_bytes(int B, int max_new_len);
+int ppv_audio_prep(const float* wav, int64_t wav_ld, const int32_t* iparams, const float* fparams, const float* noise, int B,
+                   int max_new_len, float target_db, int normalize, int Lout, float* out, void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Verification metrics and enrol-DB retrieval on the device.  Replaces ppvector/metric/metrics.py:4-37
+ * (compute_fnr_fpr / compute_eer / compute_dcf, called by ppvector/trainer.py:424-431) and the arg-max of
+ * ppvector/predict.py:173-187 (__retrieval).
+ * ------------------------------------------------------------------------------------------- */
+size_t ppv_eer_workspace_bytes(int64_t n);
+/* scores [n] fp32, labels [n] int32 (1 = target trial) -> out4 (device double[4]) = {EER, threshold at the EER, minDCF, number of targets}. */
+int ppv_eer_mindcf(const float* scores, const int32_t* labels, int64_t n, double p_target, double c_miss, double c_fa, double* out4,
+                   void* ws, size_t ws_bytes, void* stream);
+/* The evaluation loop's form (trainer.py:416-423): scores [M,N] of trials x enrolments, label = (trial_labels[i] == enroll_labels[j]). */
+int ppv_eer_mindcf_matrix(const float* scores, const int32_t* trial_labels, const int32_t* enroll_labels, int M, int N, double p_target,
+                          double c_miss, double c_fa, double* out4, void* ws, size_t ws_bytes, void* stream);
+/* sim [rows, cols] fp32 -> idx [rows] (first maximum, like numpy.argmax), best [rows]. */
+int ppv_row_argmax(const float* sim, int rows, int cols, int32_t* idx, float* best, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Cosine classifier + AAMLoss.  Replaces ppvector/models/fc.py:41-53 (Cosine, num_blocks=0) and

@@ -85,6 +85,10 @@ def test_every_shipped_config_builds_its_backbone():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     seen = {}
     for path in sorted(glob.glob(os.path.join(root, "configs", "*.yml"))):
+        if os.path.basename(path) == "augmentation.yml":  # the augmentation schema, not a model config
+            aug = yaml.load(open(path), Loader=yaml.FullLoader)
+            assert set(aug) == {"speed", "volume", "noise", "reverb", "spec_aug"}
+            continue
         cfg = dict_to_object(yaml.load(open(path), Loader=yaml.FullLoader))
         for key in ("dataset_conf", "preprocess_conf", "model_conf", "loss_conf", "optimizer_conf", "train_conf"):
             assert key in cfg, (path, key)

@@ -4,8 +4,8 @@ gradient all-reduce per step runs over NCCL."""
 from cli_common import init_distributed_if_launched, parse_options
 
 OPTIONS = [
-    ('configs', str, 'configs/ecapa_tdnn.yml', 'model / data configuration (YAML)'),
-    ('data_augment_configs', str, None, 'augmentation configuration (YAML); only its spec_aug section is implemented'),
+    ('configs', str, 'configs/cam++.yml', 'model / data configuration (YAML); the CUDA training step exists for configs/ecapa_tdnn.yml'),
+    ('data_augment_configs', str, 'configs/augmentation.yml', 'augmentation configuration (YAML): speed / volume / noise / spec_aug on the GPU'),
     ('use_gpu', bool, True, 'must stay True: this build has no CPU path'),
     ('do_eval', bool, True, 'evaluate on the enrolment / trials lists after every epoch'),
     ('save_model_path', str, 'models/', 'where checkpoints are written'),

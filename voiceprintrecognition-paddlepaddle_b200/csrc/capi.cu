@@ -124,6 +124,23 @@ int ppv_fbank_forward(ppv_fbank_t* h, const float* wav, const float* lens_ratio,
     PPV_GUARD_END
 }
 
+int ppv_fbank_forward_ragged(ppv_fbank_t* h, const float* wav, const int32_t* valid_frames, int B, int L, float* out, void* stream) {
+    PPV_GUARD_BEGIN
+    PPV_REQUIRE(h && wav && out && valid_frames, "ppv_fbank_forward_ragged: null argument");
+    PPV_REQUIRE(B > 0 && L > 0, "ppv_fbank_forward_ragged: empty input");
+    return fbank_run(h->impl, wav, nullptr, B, L, out, out, Planes(), 0, 0, static_cast<cudaStream_t>(stream), valid_frames);
+    PPV_GUARD_END
+}
+
+size_t ppv_audio_prep_workspace_bytes(int B, int max_new_len) { return audio_prep_workspace_bytes(B, max_new_len); }
+int ppv_audio_prep(const float* wav, int64_t wav_ld, const int32_t* iparams, const float* fparams, const float* noise, int B, int max_new_len,
+                   float target_db, int normalize, int Lout, float* out, void* ws, size_t ws_bytes, void* stream) {
+    PPV_GUARD_BEGIN
+    return audio_prep(wav, wav_ld, iparams, fparams, noise, B, max_new_len, target_db, normalize, Lout, out, ws, ws_bytes,
+                      static_cast<cudaStream_t>(stream));
+    PPV_GUARD_END
+}
+
 // ---------------------------------------------------------------- model
 void ppv_ecapa_default_cfg(ppv_ecapa_cfg* c) {
     if (!c) return;
@@ -268,6 +285,28 @@ int ppv_model_read_tap(ppv_model_t* h, const char* name, float* out, size_t out_
     if (h->eres) return eres2net_read_tap(h->eres, name, out, out_elems, static_cast<cudaStream_t>(stream));
     if (h->campp) return campplus_read_tap(h->campp, name, out, out_elems, static_cast<cudaStream_t>(stream));
     return ecapa_read_tap(h->ecapa, name, out, out_elems, static_cast<cudaStream_t>(stream));
+    PPV_GUARD_END
+}
+
+size_t ppv_eer_workspace_bytes(int64_t n) { return eer_workspace_bytes(n); }
+int ppv_eer_mindcf(const float* scores, const int32_t* labels, int64_t n, double p_target, double c_miss, double c_fa, double* out4, void* ws,
+                   size_t ws_bytes, void* stream) {
+    PPV_GUARD_BEGIN
+    PPV_REQUIRE(labels, "ppv_eer_mindcf: null labels");
+    return eer_mindcf(scores, labels, nullptr, nullptr, 0, n, p_target, c_miss, c_fa, out4, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+    PPV_GUARD_END
+}
+int ppv_eer_mindcf_matrix(const float* scores, const int32_t* trial_labels, const int32_t* enroll_labels, int M, int N, double p_target,
+                          double c_miss, double c_fa, double* out4, void* ws, size_t ws_bytes, void* stream) {
+    PPV_GUARD_BEGIN
+    PPV_REQUIRE(trial_labels && enroll_labels && M > 0 && N > 0, "ppv_eer_mindcf_matrix: bad argument");
+    return eer_mindcf(scores, nullptr, trial_labels, enroll_labels, N, int64_t(M) * N, p_target, c_miss, c_fa, out4, ws, ws_bytes,
+                      static_cast<cudaStream_t>(stream));
+    PPV_GUARD_END
+}
+int ppv_row_argmax(const float* sim, int rows, int cols, int32_t* idx, float* best, void* stream) {
+    PPV_GUARD_BEGIN
+    return row_argmax(sim, rows, cols, idx, best, static_cast<cudaStream_t>(stream));
     PPV_GUARD_END
 }
 

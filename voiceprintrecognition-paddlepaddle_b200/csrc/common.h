@@ -243,7 +243,12 @@ void fbank_destroy(Fbank* h);
 int fbank_num_frames(const Fbank* h, int L);
 int fbank_n_mels(const Fbank* h);
 int fbank_run(Fbank* h, const float* wav, const float* lens_ratio, int B, int L, float* raw, float* out_f32,
-              const Planes& out_pl, int P, int Tp, cudaStream_t st);
+              const Planes& out_pl, int P, int Tp, cudaStream_t st, const int* valid_frames = nullptr);
+
+// ---- audio_prep.cu ----------------------------------------------------------------------------------
+size_t audio_prep_workspace_bytes(int B, int max_new_len);
+int audio_prep(const float* wav, int64_t wav_ld, const int32_t* iparams, const float* fparams, const float* noise, int B, int max_new_len,
+               float target_db, int normalize, int Lout, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
 
 // ---- spectral.cu ------------------------------------------------------------------------------------
 struct Spectral;
@@ -350,6 +355,12 @@ int aam_forward(const float* emb, const float* W, const int64_t* labels, int B, 
 int aam_backward(const float* emb, const float* W, const int64_t* labels, const float* logits, int B, int D, int S, float margin,
                  float scale, int easy_margin, float label_smoothing, float* d_emb, float* d_W, void* ws, size_t ws_bytes,
                  cudaStream_t st);
+
+// ---- metrics.cu -------------------------------------------------------------------------------------
+size_t eer_workspace_bytes(int64_t n);
+int eer_mindcf(const float* scores, const int32_t* labels, const int32_t* row_labels, const int32_t* col_labels, int ncols, int64_t n,
+               double p_target, double c_miss, double c_fa, double* out, void* ws, size_t ws_bytes, cudaStream_t st);
+int row_argmax(const float* sim, int rows, int cols, int32_t* idx, float* best, cudaStream_t st);
 
 int device_sm_count();
 

@@ -10,7 +10,12 @@
 //   * the nine taps are the SAME shared-memory patch read at row offsets dh * 64 + dw: the UMMA descriptor start address
 //     moves by whole 64-byte rows (the swizzle XOR is a function of the absolute shared-memory address, as in res2conv.cu);
 //   * three M = 128 accumulator tiles cover the 384 patch rows that hold outputs; the epilogue maps a patch row back to its
-//     grid position (halo columns are computed and dropped).
+//     grid position (halo columns are computed and dropped);
+//   * an M128 x N32 x K16 MMA keeps the tensor pipe busy for ~80 cycles (measured: it is bound by the 4 KB A-operand read, not by its
+//     65 k MACs), and so does N = 64.  The split-bf16 product A_hi W_hi + A_hi W_lo + A_lo W_hi therefore runs as TWO instructions per
+//     k-step instead of three: A_hi x [W_hi | W_lo] with N = 64 (the hi and lo weight tiles of a tap are adjacent in shared memory:
+//     one 64-row B operand) into accumulator columns [0,64), and A_lo x W_hi with N = 32 into columns [0,32); the epilogue adds the
+//     two column blocks.
 // L2 -> SM traffic per output position: 512 / 372 = 1.4 rows instead of 9.
 #include <stdio.h>
 #include <stdlib.h>
@@ -33,6 +38,7 @@ constexpr int C3_PLANE_BYTES = C3_ROWS * 64;             // 32 KB per plane
 constexpr int C3_W_TILE = 32 * 64;                       // [32 out ch x 32 k] bf16 per tap per plane
 constexpr int C3_STAGES = 2;
 constexpr int C3_BN = 32;
+constexpr int C3_ACC_COLS = 64;                          // accumulator columns per tile: [hi-part | lo-part]
 static_assert((C3_OH * C3_PW) % GEMM_BM == 0, "patch rows with outputs must be whole accumulator tiles");
 
 template <int NSPLIT>
@@ -98,7 +104,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv3x3_c32_kernel(const __gr
         fence_mbar_init();
     }
     if (warp == 2) {
-        tmem_alloc(tmem_slot, 2 * C3_BN);
+        tmem_alloc(tmem_slot, 2 * C3_ACC_COLS);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -137,7 +143,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv3x3_c32_kernel(const __gr
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, C3_BN);
+        constexpr uint32_t idesc32 = make_idesc_bf16(GEMM_BM, C3_BN), idesc64 = make_idesc_bf16(GEMM_BM, 2 * C3_BN);
         mbar_wait(w_full, 0);
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase[2] = {0, 0};
@@ -149,25 +155,28 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv3x3_c32_kernel(const __gr
                 mbar_wait(tempty_bar(acc), acc_phase[acc] ^ 1u);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t d_tmem = tmem_base + acc * C3_BN;
+                    const uint32_t d_tmem = tmem_base + acc * C3_ACC_COLS;
                     uint32_t accumulate = 0;
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
                         const int roff = C3_ROW0 + t * GEMM_BM + (tap / 3 - 1) * C3_PW + (tap % 3 - 1);
                         const uint64_t a_hi = sw64_desc(slot + uint32_t(roff) * 64u);
-                        const uint64_t b_hi = sw64_desc(w_base + (tap * NP) * C3_W_TILE);
-#pragma unroll
-                        for (int k = 0; k < 2; ++k) {
-                            umma_bf16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, accumulate);
-                            accumulate = 1;
-                        }
+                        const uint64_t b_hi = sw64_desc(w_base + (tap * NP) * C3_W_TILE);  // NSPLIT 3: rows 0-31 = W_hi, rows 32-63 = W_lo
                         if (NSPLIT == 3) {
                             const uint64_t a_lo = sw64_desc(slot + C3_PLANE_BYTES + uint32_t(roff) * 64u);
-                            const uint64_t b_lo = sw64_desc(w_base + (tap * NP + 1) * C3_W_TILE);
 #pragma unroll
-                            for (int k = 0; k < 2; ++k) umma_bf16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+                            for (int k = 0; k < 2; ++k) {
+                                umma_bf16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc64, accumulate);  // [A_hi W_hi | A_hi W_lo]
+                                accumulate = 1;
+                            }
 #pragma unroll
-                            for (int k = 0; k < 2; ++k) umma_bf16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+                            for (int k = 0; k < 2; ++k) umma_bf16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc32, 1u);  // + A_lo W_hi
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 2; ++k) {
+                                umma_bf16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc32, accumulate);
+                                accumulate = 1;
+                            }
                         }
                     }
                     umma_commit(tfull_bar(acc));
@@ -198,15 +207,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv3x3_c32_kernel(const __gr
                 const int hp = ih * C3_OH + ph, wp = iw * C3_OW + pw;  // padded grid coordinates
                 int64_t row = -1;
                 if (pw >= 1 && pw <= C3_OW && ph <= C3_OH && hp <= cp.H && wp <= cp.W) row = (int64_t(b) * cp.Hp + hp) * cp.Wp + wp;
-                epilogue_tile<C3_BN>(cp.epi, nullptr, 0, C3_BN, 0, 0, tmem_base + grp * C3_BN, tfull_bar(grp), acc_phase, tempty_bar(grp), q, lane, 0,
-                                     threadIdx.x - 128, 0u, nullptr, 0, row);
+                epilogue_tile<C3_BN>(cp.epi, nullptr, 0, C3_BN, 0, 0, tmem_base + grp * C3_ACC_COLS, tfull_bar(grp), acc_phase, tempty_bar(grp), q, lane,
+                                     0, threadIdx.x - 128, 0u, nullptr, 0, row, NSPLIT == 3 ? C3_BN : 0);
                 acc_phase ^= 1u;
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 2 * C3_BN);
+    if (warp == 2) tmem_dealloc(tmem_base, 2 * C3_ACC_COLS);
 }
 
 // ------------------------------------------------------------------------------------------------ host

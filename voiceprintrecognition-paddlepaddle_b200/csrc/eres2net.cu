@@ -275,20 +275,40 @@ void er_carve(const ERes2NetModel* m, WsCarver& cv, int B, int T, ImageGeo* geo,
     eb->stem_out = cv.planes(geo[1].rows(B), m->cfg.m_channels);
     const size_t nb = m->blocks.size();
     for (auto* v : {&eb->c1, &eb->s0, &eb->s1, &eb->a, &eb->t, &eb->xo, &eb->o3, &eb->sc, &eb->out}) v->resize(nb);
+    // Buffer liveness (round 2; every buffer used to be dedicated: 45 GB at batch 256).  All of a block's buffers live on its stage's
+    // grid, and every one of them is dead when the block's add + ReLU has run: one set per STAGE, and the block output overwrites its
+    // residual input in place (elementwise).  The per-stage activation buffer survives for the bottom-up fusion.  Zero borders and the
+    // zero padding columns survive because a buffer never changes grid or column plan inside a stage.
+    Planes s_c1[5], s_s0[5], s_s1[5], s_a[5], s_t[5], s_xo[5], s_o3[5], s_act[5];
+    bool have[5] = {false, false, false, false, false};
     for (size_t i = 0; i < nb; ++i) {
         const EBlockW& bw = m->blocks[i];
-        const int64_t R = geo[bw.stage].rows(B);
-        eb->c1[i] = cv.planes(R, 2 * bw.width);
-        eb->s0[i] = cv.planes(R, bw.wpad);
-        eb->s1[i] = cv.planes(R, bw.wpad);
-        if (bw.fuse) {
-            eb->a[i] = cv.planes(R, std::max(bw.width / 4, 32));
-            eb->t[i] = cv.planes(R, bw.width);
-            eb->xo[i] = cv.planes(R, bw.width);
+        const int st = bw.stage;
+        const int64_t R = geo[st].rows(B);
+        if (!have[st]) {
+            have[st] = true;
+            s_c1[st] = cv.planes(R, 2 * bw.width);
+            s_s0[st] = cv.planes(R, bw.wpad);
+            s_s1[st] = cv.planes(R, bw.wpad);
+            if (bw.fuse) {
+                s_a[st] = cv.planes(R, std::max(bw.width / 4, 32));
+                s_t[st] = cv.planes(R, bw.width);
+                s_xo[st] = cv.planes(R, bw.width);
+            }
+            s_o3[st] = cv.planes(R, 2 * bw.planes);
+            s_act[st] = cv.planes(R, 2 * bw.planes);
         }
-        eb->o3[i] = cv.planes(R, 2 * bw.planes);
-        if (bw.has_sc) eb->sc[i] = cv.planes(R, 2 * bw.planes);
-        eb->out[i] = cv.planes(R, 2 * bw.planes);
+        eb->c1[i] = s_c1[st];
+        eb->s0[i] = s_s0[st];
+        eb->s1[i] = s_s1[st];
+        if (bw.fuse) {
+            eb->a[i] = s_a[st];
+            eb->t[i] = s_t[st];
+            eb->xo[i] = s_xo[st];
+        }
+        eb->o3[i] = s_o3[st];
+        if (bw.has_sc) eb->sc[i] = s_act[st];
+        eb->out[i] = s_act[st];
     }
     for (int i = 0; i < 3; ++i) {
         const int64_t R = geo[i + 2].rows(B);

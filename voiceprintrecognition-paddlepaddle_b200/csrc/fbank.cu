@@ -133,7 +133,8 @@ __host__ __device__ inline FbankSmem fbank_smem_layout(int nnz, int n_mels, int 
 template <bool VEC, int WIN>
 __global__ void __launch_bounds__(FB_THREADS, 3)
     fbank_logmel_kernel(const float* __restrict__ wav, int B, int L, int T, int win_rt, int shift, int n_mels, float preemph,
-                        float log_floor, FbankTables tb, int use_tma, float* __restrict__ out_raw, float* __restrict__ part) {
+                        float log_floor, FbankTables tb, int use_tma, float* __restrict__ out_raw, float* __restrict__ part,
+                        const int* __restrict__ valid_frames) {
     extern __shared__ __align__(128) uint8_t fb_smem[];
     const int win = WIN > 0 ? WIN : win_rt;
     const FbankSmem lay = fbank_smem_layout(tb.nnz, n_mels, win, shift);
@@ -334,8 +335,10 @@ __global__ void __launch_bounds__(FB_THREADS, 3)
             for (int i = tid; i < cnt; i += FB_THREADS) dst[i] = so[i];
         }
         if (tid < n_mels) {
+            // ragged batches: frames beyond the utterance's own count are padding and stay out of its time mean
+            const int nsum = valid_frames ? max(0, min(nf, valid_frames[b] - f0)) : nf;
             float sum = 0.f;
-            for (int f = 0; f < nf; ++f) sum += so[f * n_mels + tid];
+            for (int f = 0; f < nsum; ++f) sum += so[f * n_mels + tid];
             part[int64_t(it) * FB_MAX_MELS + tid] = sum;
         }
     }
@@ -355,7 +358,7 @@ __global__ void __launch_bounds__(128) fbank_part_reduce_kernel(const float* __r
 // mean[b][f] = (sum over the utterance's nsum partial rows) / T.
 __global__ void __launch_bounds__(256)
     fbank_finalize_kernel(const float* __restrict__ raw, const float* __restrict__ part, int nsum, const float* __restrict__ lens_ratio,
-                          int B, int T, int F, float* out_f32, Planes out_pl, int P, int Tp) {
+                          const int* __restrict__ valid_frames, int B, int T, int F, float* out_f32, Planes out_pl, int P, int Tp) {
     __shared__ float s_mu[FB_MAX_MELS];
     griddep_launch_dependents();
     griddep_wait();
@@ -364,12 +367,13 @@ __global__ void __launch_bounds__(256)
         float s = 0.f;
         if (int(threadIdx.x) < F)
             for (int i = 0; i < nsum; ++i) s += part[(int64_t(b) * nsum + i) * FB_MAX_MELS + threadIdx.x];
-        s_mu[threadIdx.x] = s / float(T);
+        s_mu[threadIdx.x] = s / float(valid_frames ? max(1, min(T, valid_frames[b])) : T);
     }
     __syncthreads();
     const int lane = threadIdx.x & 31;
     int keep_n = T;
     if (lens_ratio) keep_n = int(lens_ratio[b] * float(T));  // featurizer.py:51: (ratio * T).astype(int32)
+    if (valid_frames) keep_n = min(keep_n, valid_frames[b]);
     for (int t = blockIdx.x * FB_FIN_FRAMES + (threadIdx.x >> 5); t < min(T, (int(blockIdx.x) + 1) * FB_FIN_FRAMES); t += 8) {
         const int64_t frame = int64_t(b) * T + t;
         const bool keep = t < keep_n;
@@ -523,7 +527,7 @@ int fbank_n_mels(const Fbank* h) { return h->cfg.n_mels; }
 
 // raw: scratch [B,T,F] (may equal out_f32).  Exactly one or both of out_f32 / out_pl.
 int fbank_run(Fbank* h, const float* wav, const float* lens_ratio, int B, int L, float* raw, float* out_f32,
-              const Planes& out_pl, int P, int Tp, cudaStream_t st) {
+              const Planes& out_pl, int P, int Tp, cudaStream_t st, const int* valid_frames) {
     PPV_REQUIRE(h && wav && raw, "fbank_run: null argument");
     PPV_REQUIRE(B > 0, "fbank_run: empty batch");
     const int T = fbank_num_frames(h, L);
@@ -549,7 +553,7 @@ int fbank_run(Fbank* h, const float* wav, const float* lens_ratio, int B, int L,
         float* r = raw + int64_t(b0) * T * F;
         const int grid = std::min(nb * nitem, 3 * sms);
         PPV_PDL_OK(launch_pdl(kern, dim3(grid), dim3(FB_THREADS), size_t(lay.total), st, w, nb, L, T, h->win, h->shift, F, h->cfg.preemph,
-                              h->cfg.log_floor, h->tb, use_tma, r, h->part),
+                              h->cfg.log_floor, h->tb, use_tma, r, h->part, valid_frames ? valid_frames + b0 : (const int*)nullptr),
                    "fbank_logmel_kernel");
         const float* sums = h->part;
         int nsum = nitem;
@@ -564,7 +568,7 @@ int fbank_run(Fbank* h, const float* wav, const float* lens_ratio, int B, int L,
             pl.base += int64_t(b0) * Tp * pl.ld;
         }
         PPV_PDL_OK(launch_pdl(fbank_finalize_kernel, dim3((T + FB_FIN_FRAMES - 1) / FB_FIN_FRAMES, nb), dim3(256), 0, st, (const float*)r, sums,
-                              nsum, lens_ratio ? lens_ratio + b0 : (const float*)nullptr, nb, T, F,
+                              nsum, lens_ratio ? lens_ratio + b0 : (const float*)nullptr, valid_frames ? valid_frames + b0 : (const int*)nullptr, nb, T, F,
                               out_f32 ? out_f32 + int64_t(b0) * T * F : (float*)nullptr, pl, P, Tp),
                    "fbank_finalize_kernel");
     }

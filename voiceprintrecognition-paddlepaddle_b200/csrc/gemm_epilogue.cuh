@@ -90,7 +90,7 @@ template <int BN>
 __device__ __forceinline__ void epilogue_tile(const Epilogue& ep, const CUtensorMap* map_out, int M, int N, int m0, int n0,
                                               uint32_t tmem_acc, uint32_t tfull_bar, uint32_t acc_phase, uint32_t tempty_bar, int q,
                                               int lane, int ehalf, int etid, uint32_t staging, uint8_t* staging_gen, int64_t out_row_shift = 0,
-                                              int64_t row_override = INT64_MIN) {
+                                              int64_t row_override = INT64_MIN, int sum_cols = 0) {
     // row bookkeeping
     const int rloc = q * 32 + lane;  // row within the tile == TMEM lane
     // row_override (conv3x3.cu): the caller maps this accumulator lane to its GEMM row itself (-1: the lane holds no output)
@@ -180,6 +180,13 @@ __device__ __forceinline__ void epilogue_tile(const Epilogue& ep, const CUtensor
         __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the divergent stores
         tmem_ld32(t_addr + c * 32, v);
         tmem_ld_wait();
+        if (sum_cols) {  // the accumulator is split in two column blocks `sum_cols` apart (conv3x3.cu: A_hi x [W_hi | W_lo]): add them
+            uint32_t v2[32];
+            tmem_ld32(t_addr + c * 32 + sum_cols, v2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+        }
         const int col = n0 + c * 32;
         if (!valid || col >= N || ep.debug_nostore) continue;
         float x[32];

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(RC_THREADS, 1) res2chain_kernel(const __grid_c
         fence_mbar_init();
     }
     if (warp == 2) {
-        tmem_alloc(tmem_slot, 256);
+        tmem_alloc(tmem_slot, 512);  // 3 accumulator tiles x (64 + 64) columns: [A_hi W_hi + A_lo W_hi | A_hi W_lo]
         tmem_relinquish();
     }
     tc_fence_before();
@@ -144,7 +144,10 @@ __global__ void __launch_bounds__(RC_THREADS, 1) res2chain_kernel(const __grid_c
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN);
+        // split-bf16 product as TWO instructions per k-step (see conv3x3.cu): A_hi x [W_hi | W_lo] with N = 128 -- the hi and lo weight
+        // tiles of a tap are adjacent in shared memory -- and A_lo x W_hi with N = 64; an N = 64 MMA is bound by its A-operand read,
+        // so the N = 128 one costs the same.  The epilogue adds the two 64-column blocks.
+        constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN), idesc2 = make_idesc_bf16(GEMM_BM, 2 * BN);
         int g = 0, u = 0;
         uint32_t aready_count = 0;
         for (int b = blockIdx.x; b < cp.B; b += gridDim.x, ++u) {
@@ -160,7 +163,7 @@ __global__ void __launch_bounds__(RC_THREADS, 1) res2chain_kernel(const __grid_c
                     if (g > 0) mbar_wait(tempty(t), uint32_t(g - 1) & 1u);  // epilogue drained this accumulator
                     tc_fence_after();
                     if (lane == 0) {
-                        const uint32_t d_tmem = tmem_base + t * BN;
+                        const uint32_t d_tmem = tmem_base + t * 2 * BN;
                         uint32_t accumulate = 0;
 #pragma unroll
                         for (int tap = 0; tap < 3; ++tap) {
@@ -169,16 +172,13 @@ __global__ void __launch_bounds__(RC_THREADS, 1) res2chain_kernel(const __grid_c
                             const uint64_t b_hi = make_sw128_kmajor_desc(w_base + (tap * NP) * RC_W_TILE);
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                umma_bf16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, accumulate);
+                                umma_bf16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, NSPLIT == 3 ? idesc2 : idesc, accumulate);
                                 accumulate = 1;
                             }
                             if (NSPLIT == 3) {
                                 const uint64_t a_lo = make_sw128_kmajor_desc(a_base + RC_A_PLANE + roff * 128u);
-                                const uint64_t b_lo = make_sw128_kmajor_desc(w_base + (tap * NP + 1) * RC_W_TILE);
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
                             }
                         }
                         umma_commit(tfull(t));
@@ -268,7 +268,14 @@ __global__ void __launch_bounds__(RC_THREADS, 1) res2chain_kernel(const __grid_c
                     tc_fence_after();
                     uint32_t v[16];
                     __syncwarp();
-                    tmem_ld16(tmem_base + t * BN + c0 + (uint32_t(q * 32) << 16), v);
+                    tmem_ld16(tmem_base + t * 2 * BN + c0 + (uint32_t(q * 32) << 16), v);
+                    if (NSPLIT == 3) {  // + the A_hi W_lo block
+                        uint32_t v2[16];
+                        tmem_ld16(tmem_base + t * 2 * BN + BN + c0 + (uint32_t(q * 32) << 16), v2);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) v[k] = __float_as_uint(__uint_as_float(v[k]) + __uint_as_float(v2[k]));
+                    }
                     tmem_ld_wait();
                     tc_fence_before();
                     mbar_arrive(tempty(t));  // values are in registers: the accumulator may be reused
@@ -337,7 +344,7 @@ __global__ void __launch_bounds__(RC_THREADS, 1) res2chain_kernel(const __grid_c
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 256);
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
 int res2chain_build(Res2ChainParams* cp, const Planes& x, const Planes& y, const Planes* W, const float* const* bias, const float* const* bn_scale,

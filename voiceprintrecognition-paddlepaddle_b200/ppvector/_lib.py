@@ -49,6 +49,7 @@ class ERes2NetCfg(C.Structure):
 PPV_MODEL_CAMPPLUS = 4
 PPV_SPEC_SPECTROGRAM, PPV_SPEC_MEL, PPV_SPEC_LOGMEL, PPV_SPEC_MFCC = 1, 2, 3, 4
 PPV_SPECAUG_NPARAM = 16
+PPV_PREP_NI, PPV_PREP_NF = 8, 4
 
 
 class SpectralCfg(C.Structure):
@@ -113,6 +114,13 @@ SIGNATURES = {
     "ppv_cosine_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "ppv_cosine_matrix": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_size_t, _P]),
     "ppv_cosine_pairlist": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, _P, _P]),
+    "ppv_fbank_forward_ragged": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P]),
+    "ppv_audio_prep_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "ppv_audio_prep": (C.c_int, [_P, C.c_int64, _P, _P, _P, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, _P, _P, C.c_size_t, _P]),
+    "ppv_eer_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "ppv_eer_mindcf": (C.c_int, [_P, _P, C.c_int64, C.c_double, C.c_double, C.c_double, _P, _P, C.c_size_t, _P]),
+    "ppv_eer_mindcf_matrix": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, _P, _P, C.c_size_t, _P]),
+    "ppv_row_argmax": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
     "ppv_aam_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "ppv_aam_forward": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float,
                                   _P, _P, _P, C.c_size_t, _P]),

@@ -50,3 +50,23 @@ def cosine_pairlist(E, idx):
         _lib.check(_lib.load().ppv_cosine_pairlist(_lib.ptr(E), _lib.ptr(idx), P, n, D, _lib.ptr(out), _lib.current_stream()),
                    'ppv_cosine_pairlist')
     return out
+
+
+def retrieval(features, db_features, threshold, names=None):
+    """Enrol-DB lookup of ppvector/predict.py:173-187 (``__retrieval``): cosine of each query against the per-user mean embeddings,
+    arg-max per query, accepted when the similarity reaches ``threshold``.  features [Q,D], db_features [U,D] ->
+    list of [name_or_index, similarity rounded to 5 places] or [None, None] -- scoring and arg-max on the GPU
+    (``ppv_cosine_matrix`` + ``ppv_row_argmax``)."""
+    sim = cosine_matrix(features, db_features)
+    Q, U = sim.shape
+    idx = torch.empty((Q,), dtype=torch.int32, device=sim.device)
+    best = torch.empty((Q,), dtype=torch.float32, device=sim.device)
+    with torch.cuda.device(sim.device):
+        _lib.check(_lib.load().ppv_row_argmax(_lib.ptr(sim), Q, U, _lib.ptr(idx), _lib.ptr(best), _lib.current_stream()), 'ppv_row_argmax')
+    out = []
+    for i, s in zip(idx.cpu().tolist(), best.cpu().tolist()):
+        if s >= threshold:
+            out.append([names[i] if names is not None else i, round(float(s), 5)])
+        else:
+            out.append([None, None])
+    return out

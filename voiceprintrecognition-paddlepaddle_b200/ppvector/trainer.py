@@ -1,8 +1,8 @@
 """PPVectorTrainer -- drop-in for ppvector/trainer.py:33-474 (feature extraction, training, evaluation).
 
 ``extract_features`` (trainer.py:134-157) and ``evaluate`` (trainer.py:367-447) keep their signatures, list-file formats and
-return values; featurisation, the backbone and the trial x enrol cosine matrix run on the GPU through libppv_b200, EER /
-minDCF stay host numpy.  ``train`` (trainer.py:281-365 with the step of :206-229) runs the CUDA training step of
+return values; featurisation, the backbone, the trial x enrol cosine matrix and EER / minDCF (radix sort + sweep) run on the GPU
+through libppv_b200.  ``train`` (trainer.py:281-365 with the step of :206-229) runs the CUDA training step of
 ``ppvector.train_engine.TrainEngine`` (train-mode forward, AAM loss, backward, one gradient all-reduce over NCCL, Adam) with the
 reference's schedules; it is implemented for EcapaTdnn + AAMLoss + Adam + WarmupCosineSchedulerLR (configs/ecapa_tdnn.yml) and
 raises for other combinations.  Checkpoints follow the reference's directory layout (``<model>_<feature>/{epoch_N,last_model,best_model}``
@@ -21,7 +21,7 @@ from ppvector.data_utils.collate_fn import collate_fn
 from ppvector.data_utils.featurizer import AudioFeaturizer
 from ppvector.data_utils.reader import PPVectorDataset
 from ppvector.metric.cosine import cosine_matrix
-from ppvector.metric.metrics import compute_dcf, compute_eer, compute_fnr_fpr
+from ppvector.metric.metrics import compute_dcf, compute_eer, compute_fnr_fpr, eer_mindcf_from_matrix_gpu  # noqa: F401
 from ppvector.models import build_model
 from ppvector.utils.checkpoint import find_resume_dir, load_checkpoint_dir, load_state_dict_file, save_checkpoint
 from ppvector.utils.utils import dict_to_object, print_arguments
@@ -103,8 +103,8 @@ class PPVectorTrainer(object):
         for i in tqdm(range(0, len(dataset), batch_size), desc=desc):
             if self.stop_eval:
                 break
-            batch = [dataset[j] for j in range(i, min(i + batch_size, len(dataset)))]
-            features, label, _input_lens = collate_fn(batch)  # input_lens never reaches the model (trainer.py:392-395)
+            # one launch sequence per batch (audio prep -> ragged Fbank); input_lens never reaches the model (trainer.py:392-395)
+            features, label, _input_lens = dataset.load_batch(range(i, min(i + batch_size, len(dataset))))
             feats.append(self.model(features))
             labels.append(label)
         return torch.cat(feats, dim=0), torch.cat(labels).numpy().astype(np.int32)
@@ -118,12 +118,9 @@ class PPVectorTrainer(object):
         if self.stop_eval:
             return -1, -1, -1
         # the reference scores one trial against all enrolments per Python iteration (trainer.py:416-423): one GEMM here
-        scores = cosine_matrix(trials_features, enroll_features).cpu().numpy().astype(np.float32)
-        all_score = scores.reshape(-1)
-        all_labels = (trials_labels[:, None] == enroll_labels[None, :]).astype(np.int32).reshape(-1)
-        fnr, fpr, thresholds = compute_fnr_fpr(all_score, all_labels)
-        eer, threshold = compute_eer(fnr, fpr, all_score)
-        min_dcf = compute_dcf(fnr, fpr)
+        scores = cosine_matrix(trials_features, enroll_features)
+        # EER / minDCF on the device too (metrics.py:4-37 definitions; csrc/metrics.cu): the M x N scores never visit the host
+        eer, min_dcf, threshold = eer_mindcf_from_matrix_gpu(scores, trials_labels, enroll_labels)
         if save_image_path:
             logger.warning('save_image_path: plotting is out of scope of the B200 hot path (ignored)')
         return float(eer), float(min_dcf), float(threshold)
@@ -138,7 +135,7 @@ class PPVectorTrainer(object):
             chunk = idx[i:i + batch_size]
             if len(chunk) < batch_size and (drop_last or len(chunk) < 2):
                 break
-            yield collate_fn([dataset[int(j)] for j in chunk])
+            yield dataset.load_batch(chunk)  # one decode loop on the host, then ONE GPU launch sequence for the whole batch
 
     def train(self, save_model_path='models/', log_dir='log/', resume_model=None, pretrained_model=None, do_eval=True, max_steps=None):
         """reference: trainer.py:281-365.  ``max_steps`` (extension) stops early -- used by the tests and the bench tool.
@@ -169,7 +166,7 @@ class PPVectorTrainer(object):
         fz = self._featurizer()
         dataset_args = dict(cf.dataset_conf.get('dataset', {}))
         train_dataset = PPVectorDataset(data_list_path=cf.dataset_conf.train_list, audio_featurizer=fz, mode='train', device=self.device,
-                                        aug_conf=self.data_augment_configs, **dataset_args)
+                                        aug_conf=self.data_augment_configs, num_speakers=int(cf.model_conf.classifier.num_speakers), **dataset_args)
         sampler = cf.dataset_conf.get('sampler', {})
         batch_size = int(sampler.get('batch_size', 64))
         num_speakers = int(cf.model_conf.classifier.num_speakers)
