@@ -297,7 +297,15 @@ int ppv_row_argmax(const float* sim, int rows, int cols, int32_t* idx, float* be
  * ppvector/loss/aamloss.py:28-46 (mean softmax-CE over scale * margin-adjusted cosines).
  * W is [D,S] (Paddle layout, fc.py:31).  logits [B,S] receives the plain cosines
  * (outputs['logits'] of the reference); loss is a device scalar.
+ * The `easy_margin` argument selects the loss head: 0 = AAMLoss, 1 = AAMLoss(easy_margin=True), PPV_HEAD_AM = AMLoss
+ * (ppvector/loss/amloss.py:18-24), PPV_HEAD_ARM = ARMLoss (armloss.py:18-31), PPV_HEAD_CE = CELoss (celoss.py:16-18: raw logits,
+ * `scale` ignored); label smoothing and the mean over the batch are common to all of them.
  * ------------------------------------------------------------------------------------------- */
+#define PPV_HEAD_AAM 0
+#define PPV_HEAD_AAM_EASY 1
+#define PPV_HEAD_AM 2
+#define PPV_HEAD_ARM 3
+#define PPV_HEAD_CE 4
 int ppv_aam_forward(const float* emb, const float* W, const int64_t* labels, int B, int D, int S, float margin,
                     float scale, int easy_margin, float label_smoothing, float* logits, float* loss,
                     void* ws, size_t ws_bytes, void* stream);

@@ -90,3 +90,21 @@ def cosine_pairlist(E: np.ndarray, idx: np.ndarray) -> np.ndarray:
     E = np.asarray(E, dtype=np.float64)
     En = E / np.linalg.norm(E, axis=1, keepdims=True)
     return np.einsum("pd,pd->p", En[idx[:, 0]], En[idx[:, 1]])
+
+
+def margin_head_loss(logits: torch.Tensor, labels: torch.Tensor, kind: str, margin=0.2, scale=30.0, label_smoothing=0.0) -> torch.Tensor:
+    """The reference's other softmax heads over the cosine logits:
+      'AM'  ppvector/loss/amloss.py:18-24    predictions = scale * (logits - margin * onehot)
+      'ARM' ppvector/loss/armloss.py:18-31   as AM, then entries below their row's target value are replaced by 0
+      'CE'  ppvector/loss/celoss.py:16-18    predictions = logits
+    all with CrossEntropyLoss(reduction='sum', label_smoothing) / batch size."""
+    B = logits.shape[0]
+    if kind == "CE":
+        pred = logits
+    else:
+        one_hot = F.one_hot(labels, logits.shape[1]).to(logits.dtype)
+        pred = scale * (logits - margin * one_hot)
+        if kind == "ARM":
+            tgt = pred.gather(1, labels.view(-1, 1))
+            pred = torch.where(pred - tgt < 0.0, torch.zeros_like(pred), pred)
+    return F.cross_entropy(pred, labels, label_smoothing=label_smoothing, reduction="sum") / B

@@ -23,6 +23,9 @@ torch.set_default_dtype(torch.float64)
 
 import paddle  # noqa: E402  (the shim)
 from ppvector.loss.aamloss import AAMLoss  # noqa: E402  (the REFERENCE's files from here on)
+from ppvector.loss.amloss import AMLoss  # noqa: E402
+from ppvector.loss.armloss import ARMLoss  # noqa: E402
+from ppvector.loss.celoss import CELoss  # noqa: E402
 from ppvector.models.campplus import CAMPPlus  # noqa: E402
 from ppvector.models.ecapa_tdnn import EcapaTdnn  # noqa: E402
 from ppvector.models.eres2net import ERes2Net  # noqa: E402
@@ -173,6 +176,18 @@ def head_fixture():
         d[f"loss_{tag}"] = np.array(float(loss))
         d[f"demb_{tag}"] = e.grad.numpy()
         d[f"dW_{tag}"] = clf.weight.grad.detach().numpy().copy()
+    # the other softmax heads on the same logits: AMLoss (amloss.py), ARMLoss (armloss.py), CELoss (celoss.py)
+    for name, crit in [("AM_m0.2_ls0.0", AMLoss(margin=0.2, scale=30, label_smoothing=0.0)), ("AM_m0.35_ls0.1", AMLoss(margin=0.35, scale=30, label_smoothing=0.1)),
+                       ("ARM_m0.2_ls0.0", ARMLoss(margin=0.2, scale=30, label_smoothing=0.0)), ("ARM_m0.1_ls0.1", ARMLoss(margin=0.1, scale=30, label_smoothing=0.1)),
+                       ("CE_m0.0_ls0.0", CELoss(label_smoothing=0.0)), ("CE_m0.0_ls0.1", CELoss(label_smoothing=0.1))]:
+        e = paddle.to_tensor(emb)
+        e.requires_grad_(True)
+        clf.weight.grad = None
+        loss = crit(clf(e), paddle.to_tensor(labels))
+        loss.backward()
+        d[f"loss_{name}"] = np.array(float(loss))
+        d[f"demb_{name}"] = e.grad.numpy()
+        d[f"dW_{name}"] = clf.weight.grad.detach().numpy().copy()
     # AAMLoss.update (aamloss.py:48-53) == constructing with that margin
     crit = AAMLoss(margin=0.0, scale=32)
     crit.update(margin=0.25)

@@ -19,10 +19,14 @@ _DTYPES = {"float32": torch.float32, "float64": torch.float64, "int": torch.int3
 
 
 def _dt(d):
+    """Paddle dtype -> torch dtype.  'float32' means "the working float precision": the fixture generator runs the reference graph in
+    fp64 (torch default dtype), and a float32 temporary inside it (armloss.py:24) must not round the fixture to single precision."""
     if d is None:
         return None
     if isinstance(d, str):
-        return _DTYPES[d]
+        d = _DTYPES[d]
+    if d is torch.float32:
+        return torch.get_default_dtype()
     return d
 
 

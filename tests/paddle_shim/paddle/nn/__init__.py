@@ -266,11 +266,11 @@ class CrossEntropyLoss(Layer):
     def __init__(self, weight=None, ignore_index=-100, reduction="mean", soft_label=False, axis=-1, use_softmax=True,
                  label_smoothing=0.0, name=None):
         super().__init__()
-        assert weight is None and reduction == "mean" and not soft_label and use_softmax
-        self._ls = label_smoothing
+        assert weight is None and reduction in ("mean", "sum") and not soft_label and use_softmax
+        self._ls, self._red = label_smoothing, reduction
 
     def forward(self, input, label):  # noqa: A002
-        return TF.cross_entropy(input, label.reshape(-1).long(), label_smoothing=self._ls)
+        return TF.cross_entropy(input, label.reshape(-1).long(), label_smoothing=self._ls, reduction=self._red)
 
 
 class loss:  # noqa: N801  (paddle.nn.loss namespace, used by a loss that is out of scope)

@@ -95,3 +95,26 @@ def test_aam_config_size_vs_autograd(cuda):
     assert abs(loss.item() - ref.item()) < 2e-5 * ref.item()
     assert (x.grad.cpu().double() - e_.grad).abs().max().item() < 1e-5 * e_.grad.abs().max().item() + 1e-9
     assert (head.weight.grad.cpu().double() - w_.grad).abs().max().item() < 1e-5 * w_.grad.abs().max().item() + 1e-9
+
+
+@pytest.mark.parametrize("kind,margin,ls", [("AM", 0.2, 0.0), ("AM", 0.35, 0.1), ("ARM", 0.2, 0.0), ("ARM", 0.1, 0.1), ("CE", 0.0, 0.0), ("CE", 0.0, 0.1)])
+def test_other_softmax_heads_match_the_reference_code(cuda, golden_dir, kind, margin, ls):
+    """AMLoss / ARMLoss / CELoss (ppvector/loss/amloss.py, armloss.py, celoss.py) on the fused CUDA head against what the REFERENCE's
+    own loss classes computed (tests/golden/ref_head.npz, made by tests/golden/make_ref_fixtures.py): loss and both gradients."""
+    from ppvector.loss import AMLoss, ARMLoss, CELoss
+    from ppvector.models.fc import SpeakerIdentification
+    g = np.load(f"{golden_dir}/ref_head.npz")
+    emb = torch.from_numpy(g["emb"]).float().to(cuda).requires_grad_(True)
+    clf = SpeakerIdentification(input_dim=192, num_speakers=g["W"].shape[1]).to(cuda)
+    with torch.no_grad():
+        clf.weight.copy_(torch.from_numpy(g["W"]).float())
+    crit = {"AM": lambda: AMLoss(margin=margin, scale=30, label_smoothing=ls), "ARM": lambda: ARMLoss(margin=margin, scale=30, label_smoothing=ls),
+            "CE": lambda: CELoss(label_smoothing=ls)}[kind]()
+    loss = crit(clf(emb), torch.from_numpy(g["labels"]).to(cuda))
+    loss.backward()
+    tag = f"{kind}_m{margin}_ls{ls}"
+    assert abs(loss.item() - float(g[f"loss_{tag}"])) < 2e-5 * max(1.0, abs(float(g[f"loss_{tag}"])))
+    for got, want in ((emb.grad, g[f"demb_{tag}"]), (clf.weight.grad, g[f"dW_{tag}"])):
+        want = torch.from_numpy(want)
+        rel = (got.double().cpu() - want).norm() / want.norm()
+        assert rel < 5e-5, (tag, rel)

@@ -136,6 +136,16 @@ def test_head_and_aamloss_match_reference_code(golden_dir):
         close(w.grad.numpy(), g[f"dW_{tag}"])
     p = head.aam_params(0.25)
     close([p["cos_m"], p["sin_m"], p["th"], p["mmm"]], g["update_0.25"], 1e-15)
+    # AMLoss / ARMLoss / CELoss (loss/amloss.py, armloss.py, celoss.py)
+    for kind, margin, ls in [("AM", 0.2, 0.0), ("AM", 0.35, 0.1), ("ARM", 0.2, 0.0), ("ARM", 0.1, 0.1), ("CE", 0.0, 0.0), ("CE", 0.0, 0.1)]:
+        e = torch.from_numpy(g["emb"]).requires_grad_(True)
+        w = torch.from_numpy(g["W"]).requires_grad_(True)
+        loss = head.margin_head_loss(head.cosine_logits(e, w), labels, kind, margin=margin, scale=30.0, label_smoothing=ls)
+        loss.backward()
+        tag = f"{kind}_m{margin}_ls{ls}"
+        assert abs(loss.item() - float(g[f"loss_{tag}"])) < 1e-10, tag
+        close(e.grad.numpy(), g[f"demb_{tag}"])
+        close(w.grad.numpy(), g[f"dW_{tag}"])
 
 
 def test_train_step_matches_reference_code(golden_dir):

@@ -61,6 +61,24 @@ def main():
     t1.record()
     torch.cuda.synchronize()
     ms = t0.elapsed_time(t1) / a.steps
+    # breakdown: forward + backward | gradient all-reduce | Adam, CUDA events around each phase of the same step
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(a.steps)]
+    if world > 1:
+        dist.barrier()
+    for i in range(a.steps):
+        ev[i][0].record()
+        eng.forward_backward(x, y, margin=0.2)
+        ev[i][1].record()
+        scale = eng.all_reduce_grads()
+        ev[i][2].record()
+        eng.adam_step(lr=1e-3, weight_decay=1e-6, grad_scale=scale)
+        ev[i][3].record()
+    torch.cuda.synchronize()
+    phases = [sum(e[k].elapsed_time(e[k + 1]) for e in ev) / a.steps for k in range(3)]
+    if world > 1:
+        tp = torch.tensor(phases, device=dev)
+        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        phases = tp.tolist()
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -70,7 +88,9 @@ def main():
         print(json.dumps({"metric": "train_samples_per_s", "value": round(world * a.batch / ms * 1e3, 1), "n_gpus": world, "ms_per_step": round(ms, 3),
                           "batch_per_gpu": a.batch, "frames": a.frames, "speakers": a.speakers, "loss": float(loss),
                           "algorithmic_tflops": round(world * a.batch * 3 * 2.857e9 / (ms * 1e-3) / 1e12, 1),
-                          "workspace_GB": round(eng._ws.numel() / 2**30, 2)}))
+                          "workspace_GB": round(eng._ws.numel() / 2**30, 2),
+                          "breakdown_ms": {"forward_backward": round(phases[0], 3), "grad_all_reduce": round(phases[1], 3), "adam": round(phases[2], 3)},
+                          "all_reduce_bytes": int(eng.grads.numel() * 4)}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -95,6 +95,30 @@ __device__ __forceinline__ float aam_margin(float c, bool is_target, float cos_m
     return easy ? c : c - mmm;
 }
 
+// Scaled logit z of one (row, class) entry and dz / dcos for the loss heads of ppvector/loss/: `kind` 0 = AAMLoss (aamloss.py:34-46),
+// 1 = AAMLoss(easy_margin=True), 2 = AMLoss (amloss.py:18-24: cos - m on the target), 3 = ARMLoss (armloss.py:18-31: AMLoss, then every
+// entry whose scaled value is below the target's is set to 0), 4 = CELoss (celoss.py:16-18: the raw logits, no scale).
+__device__ __forceinline__ float head_value(float c, bool is_target, int kind, float cos_m, float sin_m, float th, float mmm, float margin,
+                                            float scale, float zy, float* dz_dc) {
+    if (kind <= 1) {
+        float d;
+        const float v = aam_margin(c, is_target, cos_m, sin_m, th, mmm, kind, &d);
+        *dz_dc = scale * d;
+        return scale * v;
+    }
+    if (kind == 4) {
+        *dz_dc = 1.f;
+        return c;
+    }
+    const float z = scale * (c - (is_target ? margin : 0.f));
+    *dz_dc = scale;
+    if (kind == 3 && !is_target && z - zy < 0.f) {
+        *dz_dc = 0.f;
+        return 0.f;
+    }
+    return z;
+}
+
 __device__ __forceinline__ float block_reduce(float v, float* s_red, bool is_max) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     v = is_max ? warp_max(v) : warp_sum(v);
@@ -109,21 +133,22 @@ __device__ __forceinline__ float block_reduce(float v, float* s_red, bool is_max
 // one block per row: loss_b and (optionally) G[b,s] = d loss / d cos[b,s]
 __global__ void __launch_bounds__(256)
     aam_row_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, int B, int S, float cos_m, float sin_m,
-                   float th, float mmm, int easy, float scale, float ls, float* __restrict__ row_loss, float* __restrict__ G) {
+                   float th, float mmm, int easy, float scale, float ls, float* __restrict__ row_loss, float* __restrict__ G, float margin) {
     __shared__ float s_red[8];
     const int b = blockIdx.x;
     const int64_t label = labels[b];
     const float* c = logits + int64_t(b) * S;
+    const float zy = scale * (c[label] - margin);  // ARMLoss: the target's scaled logit is the threshold of its row
     float mx = -INFINITY;
     for (int s = threadIdx.x; s < S; s += blockDim.x) {
         float d;
-        mx = fmaxf(mx, scale * aam_margin(c[s], s == label, cos_m, sin_m, th, mmm, easy, &d));
+        mx = fmaxf(mx, head_value(c[s], s == label, easy, cos_m, sin_m, th, mmm, margin, scale, zy, &d));
     }
     mx = block_reduce(mx, s_red, true);
     float se = 0.f, so = 0.f, tgt = 0.f;
     for (int s = threadIdx.x; s < S; s += blockDim.x) {
         float d;
-        const float o = scale * aam_margin(c[s], s == label, cos_m, sin_m, th, mmm, easy, &d);
+        const float o = head_value(c[s], s == label, easy, cos_m, sin_m, th, mmm, margin, scale, zy, &d);
         se += expf(o - mx);
         so += o;
         if (s == label) tgt = o;
@@ -138,10 +163,10 @@ __global__ void __launch_bounds__(256)
         const float invB = 1.f / float(B);
         for (int s = threadIdx.x; s < S; s += blockDim.x) {
             float d;
-            const float o = scale * aam_margin(c[s], s == label, cos_m, sin_m, th, mmm, easy, &d);
+            const float o = head_value(c[s], s == label, easy, cos_m, sin_m, th, mmm, margin, scale, zy, &d);
             const float p = expf(o - lse);
             const float t = (s == label ? (1.f - ls) : 0.f) + ls / float(S);
-            G[int64_t(b) * S + s] = (p - t) * invB * scale * d;
+            G[int64_t(b) * S + s] = (p - t) * invB * d;
         }
     }
 }
@@ -174,7 +199,7 @@ int aam_forward(const float* emb, const float* W, const int64_t* labels, int B, 
     PPV_LAUNCH_OK("aam_logits_kernel");
     float cm, sm, th, mmm;
     margin_consts(margin, &cm, &sm, &th, &mmm);
-    aam_row_kernel<<<B, 256, 0, st>>>(logits, labels, B, S, cm, sm, th, mmm, easy_margin, scale, label_smoothing, w.row_loss, nullptr);
+    aam_row_kernel<<<B, 256, 0, st>>>(logits, labels, B, S, cm, sm, th, mmm, easy_margin, scale, label_smoothing, w.row_loss, nullptr, margin);
     PPV_LAUNCH_OK("aam_row_kernel");
     aam_mean_kernel<<<1, 32, 0, st>>>(w.row_loss, B, loss);
     PPV_LAUNCH_OK("aam_mean_kernel");
@@ -239,7 +264,7 @@ int aam_backward(const float* emb, const float* W, const int64_t* labels, const 
     AamWs w = carve_aam(ws, B, D, S);  // e_hat / inv_e / inv_w are those of the forward call
     float cm, sm, th, mmm;
     margin_consts(margin, &cm, &sm, &th, &mmm);
-    aam_row_kernel<<<B, 256, 0, st>>>(logits, labels, B, S, cm, sm, th, mmm, easy_margin, scale, label_smoothing, w.row_loss, w.G);
+    aam_row_kernel<<<B, 256, 0, st>>>(logits, labels, B, S, cm, sm, th, mmm, easy_margin, scale, label_smoothing, w.row_loss, w.G, margin);
     PPV_LAUNCH_OK("aam_row_kernel(bwd)");
     const int64_t warps = int64_t(B) * D;
     aam_dehat_kernel<<<unsigned((warps + 7) / 8), 256, 0, st>>>(w.G, W, w.inv_w, B, D, S, w.dEh);

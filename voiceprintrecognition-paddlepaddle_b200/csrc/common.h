@@ -204,6 +204,10 @@ int res2chain_launch(const Res2ChainParams& cp, int precision, int num_sms, cuda
 bool res2chain_fits(int T, int P);
 void res2chain_trace_dump(const Res2ChainParams& cp);
 
+// ---- skinny linear layers on the CUDA cores (skinny.cu): [B x K] x [K x N] with one row per utterance ----------------
+bool skinny_linear_supported(int M, int N, int K, const Epilogue& ep);
+int skinny_linear_launch(const Planes& x, int x_col0, const Planes& W, int M, int N, int K, const Epilogue& ep, cudaStream_t st);
+
 // ---- fused attentive statistics pooling (asp_fused.cu) ----------------------------------------------
 struct AspFusedParams {
     CUtensorMap mapW;    // planes [2][C][K]   box {64, 128, 1}

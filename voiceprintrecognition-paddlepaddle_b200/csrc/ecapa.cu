@@ -46,7 +46,11 @@ struct KSpec {  // one K group: `ncols` columns of a source at a row offset <- w
 enum Buf { B_FEAT, B_X0, B_H, B_Y, B_Z, B_CAT, B_MFA, B_ATT, B_GSTAT, B_POOL, B_SEM, B_SEH, B_COUNT };
 
 struct Step {
-    enum Kind { GEMM, RES2, RES2CHAIN, SE_SQUEEZE, SE_SCALE, ASP_GLOBAL, ASP_FUSED, POOL_STATS } kind;
+    enum Kind { GEMM, SKINNY, RES2, RES2CHAIN, SE_SQUEEZE, SE_SCALE, ASP_GLOBAL, ASP_FUSED, POOL_STATS } kind;
+    // SKINNY: one-row-per-utterance linear layer on the CUDA cores (skinny.cu)
+    Planes sk_x, sk_w;
+    int sk_col0 = 0, sk_M = 0, sk_N = 0, sk_K = 0;
+    Epilogue sk_ep;
     GemmParams gp;
     AspFusedParams ap;
     Res2Params rp;
@@ -454,6 +458,8 @@ static int build_plan(EcapaModel* m, int B, int T, void* ws, size_t ws_bytes, cu
     const bool use_res2_kernel = (w == 64) && !(r2env && r2env[0] == '1');
     const char* rcenv = getenv("PPV_RES2_CHAIN");  // 0 = one launch per Res2Net conv (res2conv.cu) instead of the fused chain
     const bool use_res2_chain = use_res2_kernel && m->scale == 8 && res2chain_fits(T, P) && !(rcenv && rcenv[0] == '0');
+    const char* skenv = getenv("PPV_SKINNY");  // 0 = the per-utterance linear layers through the tensor-core gather-GEMM (A-B timing)
+    const bool use_skinny = !(skenv && skenv[0] == '0');
     const char* bkenv = getenv("PPV_GEMM_BK32");  // experiment: 1 = 32-wide k-steps (SWIZZLE_64B) on the wide-N layers; measured slower
     const bool bk32_enabled = (bkenv && bkenv[0] == '1');
 
@@ -477,6 +483,22 @@ static int build_plan(EcapaModel* m, int B, int T, void* ws, size_t ws_bytes, cu
         if (ep.relu) {
             ep.bn_scale = cw.bn_scale;
             ep.bn_shift = cw.bn_shift;
+        }
+        // one row per utterance (SE MLP, ASP context bias, fc): every SM takes a 16 x 16 output tile on the CUDA cores instead of 2-6
+        // CTAs walking a latency-bound k-loop on the tensor cores
+        if (use_skinny && M == B && srcs.size() == 1 && srcs[0].row_off == 0 && skinny_linear_supported(M, cw.N, srcs[0].ncols, ep) &&
+            cw.Ktot == srcs[0].ncols) {
+            Step sk;
+            sk.kind = Step::SKINNY;
+            sk.sk_x = srcs[0].t;
+            sk.sk_col0 = srcs[0].col0;
+            sk.sk_w = cw.W;
+            sk.sk_M = M;
+            sk.sk_N = cw.N;
+            sk.sk_K = srcs[0].ncols;
+            sk.sk_ep = ep;
+            m->steps.push_back(sk);
+            return PPV_OK;
         }
         Step stp;
         stp.kind = Step::GEMM;
@@ -692,10 +714,12 @@ int ecapa_forward(EcapaModel* m, const float* feat, Fbank* fb, const float* wav,
     if (rc) return rc;
     for (const Step& s : m->steps) {
         const bool tensor_step = (s.kind == Step::GEMM || s.kind == Step::ASP_FUSED || s.kind == Step::RES2 || s.kind == Step::RES2CHAIN);
+        // (SKINNY steps count as "other kernels": their FLOPs are not credited to the tensor-core roofline)
         prof_mark(tensor_step ? 0 : 1, true);
         if (tensor_step) m->launches_gemm += 1; else m->launches_other += 1;
         switch (s.kind) {
             case Step::GEMM: rc = gemm_launch(s.gp, s.BN, m->precision, m->num_sms, st); break;
+            case Step::SKINNY: rc = skinny_linear_launch(s.sk_x, s.sk_col0, s.sk_w, s.sk_M, s.sk_N, s.sk_K, s.sk_ep, st); break;
             case Step::RES2: rc = res2conv_launch(s.rp, m->precision, m->num_sms, st); break;
             case Step::RES2CHAIN:
                 rc = res2chain_launch(s.cp, m->precision, m->num_sms, st);

@@ -15,6 +15,7 @@ from ppvector import _lib
 
 
 def aam_forward_raw(emb, weight, labels, margin, scale, easy_margin, label_smoothing):
+    """``easy_margin`` doubles as the head selector of the C ABI: False / True = AAMLoss, _lib.PPV_HEAD_AM / ARM / CE = the other heads."""
     _lib.require_cuda(emb, 'features')
     lib = _lib.load()
     emb = emb.to(torch.float32).contiguous()
@@ -29,7 +30,7 @@ def aam_forward_raw(emb, weight, labels, margin, scale, easy_margin, label_smoot
     ws = torch.empty(nbytes, dtype=torch.uint8, device=emb.device)
     with torch.cuda.device(emb.device):
         _lib.check(lib.ppv_aam_forward(_lib.ptr(emb), _lib.ptr(weight), _lib.ptr(labels), B, D, S, float(margin), float(scale),
-                                       int(bool(easy_margin)), float(label_smoothing), _lib.ptr(logits), _lib.ptr(loss),
+                                       int(easy_margin), float(label_smoothing), _lib.ptr(logits), _lib.ptr(loss),
                                        C.c_void_p(ws.data_ptr()), nbytes, _lib.current_stream()), 'ppv_aam_forward')
     return logits, loss, ws
 
@@ -58,7 +59,7 @@ class _AAMFunction(torch.autograd.Function):
         ws = ctx.ws
         with torch.cuda.device(emb.device):
             _lib.check(lib.ppv_aam_backward(_lib.ptr(emb), _lib.ptr(weight), _lib.ptr(labels), _lib.ptr(logits), B, D, S,
-                                            float(margin), float(scale), int(bool(easy_margin)), float(label_smoothing),
+                                            float(margin), float(scale), int(easy_margin), float(label_smoothing),
                                             _lib.ptr(d_emb), _lib.ptr(d_w), C.c_void_p(ws.data_ptr()), ws.numel(),
                                             _lib.current_stream()), 'ppv_aam_backward')
         return d_emb * grad_out, d_w * grad_out, None, None, None, None, None

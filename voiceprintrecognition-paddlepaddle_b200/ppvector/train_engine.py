@@ -89,7 +89,7 @@ class TrainEngine:
                 self._ws = torch.empty(need, dtype=torch.uint8, device=x.device)
                 self._ws_key = (B, T)
             logits = torch.empty((B, self.num_speakers), dtype=torch.float32, device=x.device) if return_logits else None
-            _lib.check(lib.ppv_trainer_forward_backward(self._h, _lib.ptr(x), _lib.ptr(y), B, T, float(margin), float(scale), int(bool(easy_margin)),
+            _lib.check(lib.ppv_trainer_forward_backward(self._h, _lib.ptr(x), _lib.ptr(y), B, T, float(margin), float(scale), int(easy_margin),
                                                         float(label_smoothing), _lib.ptr(self._loss), _lib.ptr(logits),
                                                         C.c_void_p(self._ws.data_ptr()), self._ws.numel(), _lib.current_stream()),
                        'ppv_trainer_forward_backward')

@@ -145,15 +145,15 @@ class PPVectorTrainer(object):
 
         import torch.distributed as dist
 
-        from ppvector.loss import AAMLoss
+        from ppvector.loss import build_loss
         from ppvector.optimizer import MarginScheduler, build_lr_scheduler
         from ppvector.train_engine import TrainEngine
         cf = self.configs
         use_model = cf.model_conf.get('model', 'CAMPPlus')
         if use_model != 'EcapaTdnn':
             raise NotImplementedError(f'training on the B200 path is implemented for EcapaTdnn (got {use_model}); no fallback')
-        if cf.loss_conf.get('loss', 'AAMLoss') != 'AAMLoss' or cf.optimizer_conf.get('optimizer', 'Adam') != 'Adam':
-            raise NotImplementedError('training on the B200 path implements AAMLoss + Adam (configs/ecapa_tdnn.yml)')
+        if cf.loss_conf.get('loss', 'AAMLoss') not in ('AAMLoss', 'AMLoss', 'ARMLoss', 'CELoss') or cf.optimizer_conf.get('optimizer', 'Adam') != 'Adam':
+            raise NotImplementedError('training on the B200 path implements AAMLoss / AMLoss / ARMLoss / CELoss + Adam (configs/ecapa_tdnn.yml)')
         if cf.train_conf.get('enable_amp', False):
             raise NotImplementedError('enable_amp: the B200 training step runs its fp32-grade split-bf16 path only')
         if cf.dataset_conf.get('is_use_pksampler', False):
@@ -213,8 +213,7 @@ class PPVectorTrainer(object):
             dist.broadcast(engine.stats, src=0)
         steps_per_epoch = max(1, (int(np.ceil(len(train_dataset) / world)) // batch_size))
         scheduler = build_lr_scheduler(step_per_epoch=steps_per_epoch, configs=cf)
-        loss_args = dict(cf.loss_conf.get('loss_args', {}))
-        criterion = AAMLoss(**loss_args)
+        criterion = build_loss(cf)  # loss/__init__.py:16-22
         margin_scheduler = None
         if cf.loss_conf.get('use_margin_scheduler', False):  # trainer.py:182-190: defaults overridden with dict.update
             ms_args = dict(increase_start_epoch=int(cf.train_conf.max_epoch * 0.3), fix_epoch=int(cf.train_conf.max_epoch * 0.7))
