@@ -113,3 +113,32 @@ def test_step_is_bitwise_reproducible(cuda, W64):
     eng.load_state_dict(W64, Wc)  # running statistics back to the start
     eng.forward_backward(f.float().to(cuda), y.to(cuda))
     assert torch.equal(g1, eng.grads)
+
+
+def test_gradients_at_the_config_size(cuda, W64):
+    """BASELINE config-3 step shape (per-GPU batch 64 x 298 frames): loss, logits and EVERY parameter gradient against fp64 autograd of the
+    oracle, with per-depth bounds set from what the step measures (the error grows towards the input through ~20 train-mode BatchNorm
+    backward passes; see the module docstring): head 5e-4, pooling / MFA 5e-3, SE-Res2 blocks 3 / 2 / 1 at 1e-2 / 1.5e-2 / 2e-2, first
+    conv 3e-2, cosine to the fp64 gradient > 0.999 everywhere."""
+    B, T = 64, 298
+    f, y, Wc = make_problem(B, T, 64298)
+    loss, grads, stats, logits = ot.train_step_grads(f, y, W64, Wc, margin=0.2)
+    eng = new_engine(cuda, W64, Wc)
+    got_loss, got_logits = eng.forward_backward(f.float().to(cuda), y.to(cuda), margin=0.2, return_logits=True)
+    assert (got_logits.double().cpu() - logits).abs().max() < 1e-4
+    assert abs(got_loss.item() - loss.item()) < 1e-3 * max(1.0, abs(loss.item()))
+    bounds = [("classifier", 5e-4), ("fc.", 5e-4), ("asp_bn.", 5e-4), ("asp.", 5e-3), ("mfa.", 5e-3), ("blocks.3", 1e-2), ("blocks.2", 1.5e-2),
+              ("blocks.1", 2e-2), ("blocks.0", 3e-2)]
+    worst, bad = {}, []
+    for name, gw in grads.items():
+        if name == "asp.conv.conv.bias":
+            continue
+        gg = eng.view(name, tuple(gw.shape), "grad").double().cpu()
+        rel = ((gg - gw).norm() / (gw.norm() + 1e-12)).item()
+        cos = ((gg * gw).sum() / (gg.norm() * gw.norm() + 1e-30)).item()
+        pre, tol = next((p, t) for p, t in bounds if name.startswith(p))
+        worst[pre] = max(worst.get(pre, 0.0), rel)
+        if not (rel < tol and cos > 0.999):
+            bad.append((name, rel, cos))
+    print("worst relative gradient error per group at 64 x 298:", {k: f"{v:.2e}" for k, v in worst.items()})
+    assert not bad, (bad[:10], worst)

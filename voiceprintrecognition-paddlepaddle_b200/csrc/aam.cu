@@ -272,11 +272,7 @@ int aam_backward(const float* emb, const float* W, const int64_t* labels, const 
     aam_demb_kernel<<<(B + 7) / 8, 256, 0, st>>>(w.dEh, w.e_hat, w.inv_e, B, D, d_emb);
     PPV_LAUNCH_OK("aam_demb_kernel");
     const size_t smem = size_t(B) * D * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        PPV_CUDA_OK(cudaFuncSetAttribute(aam_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    PPV_ONCE_PER_DEVICE(PPV_CUDA_OK(cudaFuncSetAttribute(aam_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)));
     aam_dw_kernel<<<(S + 127) / 128, 128, smem, st>>>(w.G, w.e_hat, W, w.inv_w, B, D, S, d_W);
     PPV_LAUNCH_OK("aam_dw_kernel");
     return PPV_OK;

@@ -33,6 +33,19 @@ int fail(int code, const std::string& msg);
         if (!(cond)) return ::ppv::fail(PPV_EINVAL, std::string(msg)); \
     } while (0)
 
+// Function attributes (the > 48 KB dynamic shared-memory opt-in) are per device: run `stmt` once per device of this process, not once
+// per process (a second GPU used by the same process would otherwise launch without the opt-in).
+#define PPV_ONCE_PER_DEVICE(stmt)                                    \
+    do {                                                             \
+        static unsigned long long _ppv_done = 0ull;                  \
+        int _ppv_dev = 0;                                            \
+        cudaGetDevice(&_ppv_dev);                                    \
+        if (!((_ppv_done >> (_ppv_dev & 63)) & 1ull)) {              \
+            stmt;                                                    \
+            _ppv_done |= 1ull << (_ppv_dev & 63);                    \
+        }                                                            \
+    } while (0)
+
 // Launch with programmatic dependent launch enabled (see ptx.cuh: griddep_wait / griddep_launch_dependents).
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
@@ -125,11 +138,13 @@ struct GemmParams {
     CUtensorMap mapA[GEMM_MAX_MAPS];
     CUtensorMap mapB;
     CUtensorMap mapOut;  // output planes, box {64, 128, 1}, SWIZZLE_128B (TMA-store epilogue)
+    CUtensorMap mapBh;   // weight planes, box {BK, BN / 2, 1}: the half tile a CTA of a cluster pair loads and multicasts (mc mode)
     KStep ksteps[GEMM_MAX_KSTEPS];
     int num_ksteps;
     int bk;  // K elements per k-step (64 or 32)
     int l2_prefetch;  // producer prefetches the next tile's activation rows into L2
     int ws;           // weight-stationary mode (set by gemm_build): W resident in shared memory, the ring carries activations only
+    int mc;           // cluster-pair mode (set by gemm_build): two CTAs take the two m-tiles of a pair and share each weight tile by TMA multicast
     int lin_splits;   // > 0: weight-gradient mode (see gemm_build_wgrad): K runs over operand columns, split in lin_splits parts
     int lin_b_row0, lin_b_col0;
     int64_t lin_split_rows;

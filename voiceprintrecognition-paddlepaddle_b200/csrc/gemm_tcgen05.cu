@@ -99,10 +99,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         prefetch_tmap(&gp.mapB);
         if (gp.epi.tma_store) prefetch_tmap(&gp.mapOut);
     }
+    // Cluster-pair mode (gp.mc): the two CTAs of a cluster work on the two m-tiles of a pair with the SAME n-tile; each loads half of
+    // every weight tile and multicasts it into both CTAs' ring slot, so a slot is free only when both CTAs' MMAs have retired
+    // (empty barriers count 2, released by multicast commits).  L2 -> SM weight traffic per CTA halves.
+    const uint32_t mc_rank = gp.mc ? cluster_ctarank() : 0u;
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), 1);
+            mbar_init(empty_bar(s), gp.mc ? 2 : 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
@@ -117,6 +121,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     }
     tc_fence_before();
     __syncthreads();
+    if (gp.mc) cluster_sync_all();  // the peer's barriers are initialised before any multicast / remote arrive can reach them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
     griddep_launch_dependents();  // PDL: the next kernel may begin its prologue
@@ -128,6 +133,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     const int mn_tiles = gp.m_tiles * gp.n_tiles;
     const int num_tiles = mn_tiles * (gp.lin_splits > 0 ? gp.lin_splits : 1);
     const int nk = gp.num_ksteps;
+    // work list of this CTA: tile_first, tile_first + tile_step, ... < tile_end.  Default: tile = m * n_tiles + n over all CTAs.
+    // mc: "pair tiles" pt = mp * n_tiles + n over the clusters; this CTA takes m = 2 * mp + rank (an odd last m-tile leaves one CTA of
+    // the last pair on rows >= M: it still loads and multicasts its weight halves; its loads are zero-filled and its stores dropped).
+    const int tile_first = gp.mc ? int(cluster_id_x()) : int(blockIdx.x);
+    const int tile_step = gp.mc ? int(num_clusters_x()) : int(gridDim.x);
+    const int tile_end = gp.mc ? ((gp.m_tiles + 1) / 2) * gp.n_tiles : num_tiles;
+    auto tile_m = [&](int t) { return gp.mc ? 2 * (t / gp.n_tiles) + int(mc_rank) : (t % mn_tiles) / gp.n_tiles; };
+    auto tile_n = [&](int t) { return gp.mc ? t % gp.n_tiles : (t % mn_tiles) % gp.n_tiles; };
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -139,15 +152,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                 for (int p = 0; p < Cfg::NB; ++p) tma_load_3d(w_res + (s * Cfg::NB + p) * Cfg::B_BYTES, &gp.mapB, w_full, s * BK, 0, p);
         }
         __syncwarp();
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int tmn = tile % mn_tiles, zsplit = tile / mn_tiles;
-            const int m0 = (tmn / gp.n_tiles) * GEMM_BM;
-            const int n0 = (tmn % gp.n_tiles) * BN;
+        for (int tile = tile_first; tile < tile_end; tile += tile_step) {
+            const int zsplit = gp.mc ? 0 : tile / mn_tiles;
+            const int m0 = tile_m(tile) * GEMM_BM;
+            const int n0 = tile_n(tile) * BN;
             // L2 prefetch of the activation rows of this CTA's NEXT tile (one CTA per m-tile issues it): they come
             // from HBM, and a 2-4 slot ring alone cannot hide that latency.
-            const int ntile = tile + gridDim.x;
-            if (gp.l2_prefetch && ntile < num_tiles && (ntile % gp.n_tiles) == 0 && lane < nk) {
-                const int nm0 = (ntile / gp.n_tiles) * GEMM_BM;
+            const int ntile = tile + tile_step;
+            if (gp.l2_prefetch && ntile < tile_end && tile_n(ntile) == 0 && lane < nk) {
+                const int nm0 = tile_m(ntile) * GEMM_BM;
                 for (int s = lane; s < nk; s += 32) {
                     const KStep ks = gp.ksteps[s];
 #pragma unroll
@@ -173,6 +186,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
 #pragma unroll
                         for (int p = 0; p < Cfg::NB; ++p)
                             tma_load_3d(sb + p * Cfg::B_BYTES, &gp.mapB, fb, kcol + gp.lin_b_col0, gp.lin_b_row0 + n0, p);
+                    } else if (gp.mc) {
+                        const KStep ks = gp.ksteps[s];
+                        const CUtensorMap* ma = &gp.mapA[ks.map];
+#pragma unroll
+                        for (int p = 0; p < Cfg::NA; ++p)
+                            tma_load_3d(sa + p * Cfg::A_BYTES, ma, fb, ks.a_col, m0 + ks.row_off, p);
+                        // this CTA's half of the weight tile (rows [rank * BN/2, +BN/2)) lands in BOTH CTAs' slot and signals both full barriers
+#pragma unroll
+                        for (int p = 0; p < Cfg::NB; ++p)
+                            tma_load_3d_mc(sb + p * Cfg::B_BYTES + mc_rank * (BN / 2) * (BK * 2), &gp.mapBh, fb, s * BK, n0 + int(mc_rank) * (BN / 2), p,
+                                           uint16_t(3));
                     } else {
                         const KStep ks = gp.ksteps[s];
                         const CUtensorMap* ma = &gp.mapA[ks.map];
@@ -199,7 +223,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         int acc = 0;
         uint32_t acc_phase = 0;
         if (gp.ws) mbar_wait(w_full, 0);
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = tile_first; tile < tile_end; tile += tile_step) {
             mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue drained this accumulator
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BN;
@@ -223,7 +247,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
                     }
-                    umma_commit(empty_bar(stage));                   // smem slot free when these MMAs retire
+                    if (gp.mc) {
+                        umma_commit_mc(empty_bar(stage), uint16_t(3));  // the slot is also the peer's multicast target
+                    } else {
+                        umma_commit(empty_bar(stage));  // smem slot free when these MMAs retire
+                    }
                     if (s == nk - 1) umma_commit(tfull_bar(acc));   // accumulator complete
                 }
                 __syncwarp();
@@ -242,12 +270,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         const int ehalf = (warp - 4) >> 2;   // two warps share a TMEM lane quarter and split the column chunks
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int tmn = tile % mn_tiles;
-            const int m0 = (tmn / gp.n_tiles) * GEMM_BM;
-            const int n0 = (tmn % gp.n_tiles) * BN;
+        for (int tile = tile_first; tile < tile_end; tile += tile_step) {
+            const int m0 = tile_m(tile) * GEMM_BM;
+            const int n0 = tile_n(tile) * BN;
             epilogue_tile<BN>(gp.epi, &gp.mapOut, gp.M, gp.N, m0, n0, tmem_base + acc * BN, tfull_bar(acc), acc_phase, tempty_bar(acc), q,
-                              lane, ehalf, etid, staging, staging_gen, int64_t(tile / mn_tiles) * gp.lin_split_rows);
+                              lane, ehalf, etid, staging, staging_gen, gp.mc ? 0 : int64_t(tile / mn_tiles) * gp.lin_split_rows);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
         }
@@ -256,6 +283,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
 
     tc_fence_before();
     __syncthreads();
+    if (gp.mc) cluster_sync_all();  // no CTA retires while its peer may still multicast into it or arrive on its barriers
     if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
@@ -355,6 +383,15 @@ int gemm_build(GemmParams* gp, const GemmSource* srcs, int nsrc, const Planes& W
                      : 0;
     }
     {
+        // cluster-pair weight multicast: wide layers (one 256-column n-tile or more, K in the k-step table, many m-tiles) that are not weight-stationary
+        const char* mcenv = getenv("PPV_GEMM_MC");
+        gp->mc = (BN == 256 && BK == 64 && !gp->ws && gp->m_tiles >= 64 && N % BN == 0 && mcenv && mcenv[0] == '1') ? 1 : 0;
+        if (gp->mc) {
+            rc = encode_planes_map_ex(&gp->mapBh, W, BK, BN / 2, BK * 2);
+            if (rc) return rc;
+        }
+    }
+    {
         const char* ns = getenv("PPV_GEMM_NOSTORE");
         gp->epi.debug_nostore = (ns && ns[0] == '1') ? 1 : 0;
         const char* pf = getenv("PPV_GEMM_NO_L2PREFETCH");
@@ -429,13 +466,29 @@ int gemm_build_wgrad(GemmParams* gp, const Planes& At, const Planes& Bt, int M, 
 template <int BN, int NSPLIT, int BK>
 static int launch_one(const GemmParams& gp, int num_sms, cudaStream_t stream) {
     using Cfg = GemmCfg<BN, NSPLIT, BK>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        PPV_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, NSPLIT, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES));
-        attr_set = true;
-    }
+    PPV_ONCE_PER_DEVICE(PPV_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, NSPLIT, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES)));
     const int tiles = gp.m_tiles * gp.n_tiles * (gp.lin_splits > 0 ? gp.lin_splits : 1);
+    if (gp.mc) {  // clusters of two CTAs; one cluster per pair tile at most
+        const int pair_tiles = ((gp.m_tiles + 1) / 2) * gp.n_tiles;
+        const int clusters = std::min(pair_tiles, num_sms / 2);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * clusters);
+        cfg.blockDim = dim3(GEMM_THREADS);
+        cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        attr[1].id = cudaLaunchAttributeClusterDimension;
+        attr[1].val.clusterDim.x = 2;
+        attr[1].val.clusterDim.y = 1;
+        attr[1].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 2;
+        PPV_PDL_OK(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, NSPLIT, BK>, gp), "gemm_tcgen05_kernel (cluster pairs)");
+        return PPV_OK;
+    }
     const int grid = std::min(tiles, num_sms);
     PPV_PDL_OK(launch_pdl(gemm_tcgen05_kernel<BN, NSPLIT, BK>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, gp),
                "gemm_tcgen05_kernel");

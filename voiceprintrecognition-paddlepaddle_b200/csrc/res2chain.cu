@@ -395,11 +395,7 @@ int res2chain_build(Res2ChainParams* cp, const Planes& x, const Planes& y, const
 template <int NSPLIT>
 static int launch_rc(const Res2ChainParams& cp, int num_sms, cudaStream_t st) {
     using Cfg = RCCfg<NSPLIT>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        PPV_CUDA_OK(cudaFuncSetAttribute(res2chain_kernel<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_set = true;
-    }
+    PPV_ONCE_PER_DEVICE(PPV_CUDA_OK(cudaFuncSetAttribute(res2chain_kernel<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)));
     const int grid = std::min(cp.B, num_sms);
     PPV_PDL_OK(launch_pdl(res2chain_kernel<NSPLIT>, dim3(grid), dim3(RC_THREADS), Cfg::SMEM_BYTES, st, cp), "res2chain_kernel");
     return PPV_OK;

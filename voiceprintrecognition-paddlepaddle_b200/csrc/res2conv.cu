@@ -221,11 +221,7 @@ int res2conv_build(Res2Params* rp, const GemmSource* srcs, int nsrc, const Plane
 template <int NSPLIT>
 static int launch_r2(const Res2Params& rp, int num_sms, cudaStream_t st) {
     using Cfg = R2Cfg<NSPLIT>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        PPV_CUDA_OK(cudaFuncSetAttribute(res2conv_kernel<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_set = true;
-    }
+    PPV_ONCE_PER_DEVICE(PPV_CUDA_OK(cudaFuncSetAttribute(res2conv_kernel<NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)));
     const int grid = std::min(rp.m_tiles, num_sms);
     PPV_PDL_OK(launch_pdl(res2conv_kernel<NSPLIT>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, st, rp), "res2conv_kernel");
     return PPV_OK;

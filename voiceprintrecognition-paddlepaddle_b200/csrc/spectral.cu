@@ -354,11 +354,7 @@ int spectral_run(Spectral* h, const float* wav, const float* lens_ratio, int B, 
     a.amin = h->cfg.amin;
     a.log_ref = h->log_ref;
     const size_t smem = size_t(h->n_fft) * sizeof(float2) + size_t(h->n_bins) * sizeof(float) + 512 * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        PPV_CUDA_OK(cudaFuncSetAttribute(spectral_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        attr_set = true;
-    }
+    PPV_ONCE_PER_DEVICE(PPV_CUDA_OK(cudaFuncSetAttribute(spectral_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)));
     PPV_REQUIRE(smem <= 64 * 1024, "spectral_run: shared memory budget exceeded");
     PPV_PDL_OK(launch_pdl(spectral_frame_kernel, dim3(T, B), dim3(SP_THREADS), smem, st, wav, L, T, h->F, a, out), "spectral_frame_kernel");
     PPV_PDL_OK(launch_pdl(spectral_cmn_kernel, dim3((h->F + 31) / 32, B), dim3(256), 0, st, out, lens_ratio, T, h->F), "spectral_cmn_kernel");
