@@ -119,7 +119,7 @@ __host__ __device__ inline FbankSmem fbank_smem_layout(int nnz, int n_mels, int 
     L.mstart = take(n_mels * 4);
     L.mlen = take(n_mels * 4);
     L.moff = take(n_mels * 4);
-    L.scr = take(FB_ITEM * FB_SCR * 8);
+    L.scr = take(FB_ITEM * FB_SCR * 8 + 64);
     L.out = take(2 * FB_ITEM * n_mels * 4);
     L.seg_stride = (((FB_ITEM - 1) * shift + win) * 4 + 127) & ~127;
     L.seg = take(2 * L.seg_stride);
@@ -190,7 +190,8 @@ __global__ void __launch_bounds__(FB_THREADS, 3)
     }
 
     const float inv_win = 1.f / float(win);
-    float2* scr = s_scr + fl * FB_SCR;
+    // the two frames of a warp sit 16 banks apart (odd slots shifted by 64 B): their 4-byte power stores / mel reads do not collide
+    float2* scr = s_scr + fl * FB_SCR + (fl & 1) * 8;
     int n = 0;
     for (int it = blockIdx.x; it < total; it += gridDim.x, ++n) {
         const int buf = n & 1;
