@@ -98,3 +98,35 @@ def test_gemm_exact_small_integers(cuda):
     for prec in (_lib.PPV_PREC_BF16X3, _lib.PPV_PREC_BF16):
         out = run_gemm(A, W, bn=64, prec=prec)
         assert torch.equal(out, A @ W.t())
+
+
+@pytest.mark.parametrize("M,N,K,bk", [(128 * 64, 256, 64, 64), (128 * 65 - 37, 512, 512, 64), (128 * 67 + 1, 256, 192, 32), (128 * 80, 1536, 320, 64)])
+@pytest.mark.parametrize("prec", [_lib.PPV_PREC_BF16X3, _lib.PPV_PREC_BF16])
+def test_gemm_pair_mode(cuda, M, N, K, bk, prec):
+    """>= 64 m-tiles with 256-wide n-tiles run as cta_group::2 pairs (256 x 256 tiles over two SMs, each CTA loads its activation rows and half
+    of the weight tile).  Odd m-tile counts leave one CTA of the last pair without rows; ragged last tiles are zero-filled by TMA."""
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(cuda)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(cuda)
+    bias = torch.randn(N, generator=g).to(cuda)
+    scale = (torch.rand(N, generator=g) + 0.5).to(cuda)
+    shift = torch.randn(N, generator=g).to(cuda)
+    out = run_gemm(A, W, bias=bias, scale=scale, shift=shift, relu=1, bn=256, prec=prec, bk=bk)
+    ref = ref_gemm(A, W, bias, scale, shift, relu=1)
+    assert torch.isfinite(out).all()
+    err = (out.double() - ref).abs().max().item()
+    tol = 2e-5 if prec == _lib.PPV_PREC_BF16X3 else 6e-2
+    assert err < tol * max(ref.abs().max().item(), 1.0), err
+
+
+def test_gemm_pair_mode_equals_single_cta(cuda, monkeypatch):
+    """PPV_GEMM_PAIR=0 keeps the same layer on single-CTA 128 x 256 tiles: identical MMA order per output element -> identical bits."""
+    g = torch.Generator(device="cpu").manual_seed(5)
+    M, N, K = 128 * 66 + 5, 512, 512
+    A = torch.randn(M, K, generator=g).to(cuda)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(cuda)
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("PPV_GEMM_PAIR", flag)
+        outs.append(run_gemm(A, W, bn=256))
+    assert torch.equal(outs[0], outs[1])

@@ -56,7 +56,8 @@ struct TransitW {
 };
 
 struct CStep {
-    enum Kind { STEM, GEMM, CONV3, ADD_RELU, FLATTEN, BN_RELU, CONTEXT, STATS } kind;
+    enum Kind { STEM, GEMM, CONV3, PW, ADD_RELU, FLATTEN, BN_RELU, CONTEXT, STATS } kind;
+    PwStep pw;  // PW: 1x1 conv with K <= 64 on the CUDA cores (pointwise.cu)
     GemmParams gp;
     Conv3x3Params c3;  // CONV3: the 32 -> 32 channel 3x3 convs of the FCM head (conv3x3.cu)
     int BN = 0;
@@ -529,6 +530,18 @@ static int cp_build_plan(CamppModel* m, int B, int T, void* ws, size_t ws_bytes,
     };
     auto add_gemm = [&](const GemmWeights& gw, const std::vector<GemmSource>& srcs, int M, Epilogue ep) -> int {
         ep.bias = gw.bias;
+        if (pointwise_enabled() && ep.img_Wp > 0 && pointwise_supported(srcs.data(), int(srcs.size()), gw.N, ep)) {
+            CStep sp;
+            sp.kind = CStep::PW;
+            for (size_t i = 0; i < srcs.size(); ++i) sp.pw.srcs[i] = srcs[i];
+            sp.pw.nsrc = int(srcs.size());
+            sp.pw.N = gw.N;
+            sp.pw.M = M;
+            sp.pw.W = gw.W;
+            sp.pw.ep = ep;
+            m->steps.push_back(sp);
+            return PPV_OK;
+        }
         CStep s;
         s.kind = CStep::GEMM;
         s.BN = cp_pick_bn(gw.N);
@@ -713,6 +726,7 @@ int campplus_forward(CamppModel* m, const float* feat, int B, int T, float* emb,
                 break;
             case CStep::GEMM: rc = gemm_launch(s.gp, s.BN, m->precision, m->num_sms, st); break;
             case CStep::CONV3: rc = conv3x3_launch(s.c3, m->precision, m->num_sms, st); break;
+            case CStep::PW: rc = pointwise_launch(s.pw, m->num_sms, st); break;
             case CStep::ADD_RELU: rc = launch_se_scale_res(s.a, nullptr, s.b, 0, s.d, 0, s.C, s.img_rows, s.rows, m->num_sms, st, 1, 0.f); break;
             case CStep::FLATTEN: {
                 const ImageGeo& g = m->geo[3];

@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <string>
@@ -138,13 +139,13 @@ struct GemmParams {
     CUtensorMap mapA[GEMM_MAX_MAPS];
     CUtensorMap mapB;
     CUtensorMap mapOut;  // output planes, box {64, 128, 1}, SWIZZLE_128B (TMA-store epilogue)
-    CUtensorMap mapBh;   // weight planes, box {BK, BN / 2, 1}: the half tile a CTA of a cluster pair loads and multicasts (mc mode)
+    CUtensorMap mapBh;   // weight planes, box {BK, BN / 2, 1}: the half tile a CTA of a cta_group::2 pair loads (pair mode)
     KStep ksteps[GEMM_MAX_KSTEPS];
     int num_ksteps;
     int bk;  // K elements per k-step (64 or 32)
     int l2_prefetch;  // producer prefetches the next tile's activation rows into L2
     int ws;           // weight-stationary mode (set by gemm_build): W resident in shared memory, the ring carries activations only
-    int mc;           // cluster-pair mode (set by gemm_build): two CTAs take the two m-tiles of a pair and share each weight tile by TMA multicast
+    int pair;         // pair mode (set by gemm_build): cta_group::2 MMAs, the two CTAs of a cluster own the two 128-row halves of a 256 x BN tile
     int lin_splits;   // > 0: weight-gradient mode (see gemm_build_wgrad): K runs over operand columns, split in lin_splits parts
     int lin_b_row0, lin_b_col0;
     int64_t lin_split_rows;
@@ -218,6 +219,23 @@ int res2chain_build(Res2ChainParams* cp, const Planes& x, const Planes& y, const
 int res2chain_launch(const Res2ChainParams& cp, int precision, int num_sms, cudaStream_t st);
 bool res2chain_fits(int T, int P);
 void res2chain_trace_dump(const Res2ChainParams& cp);
+
+// ---- 1x1 convs with K <= 64 on the CUDA cores, one thread per grid position (pointwise.cu) ----------------------------
+bool pointwise_supported(const GemmSource* srcs, int nsrc, int N, const Epilogue& ep);
+int pointwise_launch(const GemmSource* srcs, int nsrc, const Planes& W, int64_t M, int N, const Epilogue& ep, int num_sms, cudaStream_t st);
+struct PwStep {  // a planned pointwise conv (the model plans keep these next to their GemmParams)
+    GemmSource srcs[2];
+    int nsrc = 0, N = 0;
+    int64_t M = 0;
+    Planes W;
+    Epilogue ep;
+};
+inline int pointwise_launch(const PwStep& s, int num_sms, cudaStream_t st) { return pointwise_launch(s.srcs, s.nsrc, s.W, s.M, s.N, s.ep, num_sms, st); }
+// PPV_POINTWISE=0 keeps these layers on the gather-GEMM (A-B timing)
+inline bool pointwise_enabled() {
+    const char* e = getenv("PPV_POINTWISE");
+    return !(e && e[0] == '0');
+}
 
 // ---- skinny linear layers on the CUDA cores (skinny.cu): [B x K] x [K x N] with one row per utterance ----------------
 bool skinny_linear_supported(int M, int N, int K, const Epilogue& ep);

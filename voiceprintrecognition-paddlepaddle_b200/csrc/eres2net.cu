@@ -38,7 +38,8 @@ struct EFuseW {  // layerN_downsample + fuse_modeXYZ
 };
 
 struct EStep {
-    enum Kind { STEM, GEMM, CONV3, ADD_RELU, AFF_COMBINE, FLATTEN, TSTP } kind;
+    enum Kind { STEM, GEMM, CONV3, PW, ADD_RELU, AFF_COMBINE, FLATTEN, TSTP } kind;
+    PwStep pw;  // PW: 1x1 conv with K <= 64 on the CUDA cores (pointwise.cu)
     Conv3x3Params c3;  // CONV3: single-source 3x3 conv over a 32-channel (padded) chunk, conv3x3.cu
     GemmParams gp;
     int BN = 0;
@@ -367,6 +368,18 @@ static int er_build_plan(ERes2NetModel* m, int B, int T, void* ws, size_t ws_byt
     };
     auto add_gemm = [&](const GemmWeights& gw, const std::vector<GemmSource>& srcs, int M, Epilogue ep) -> int {
         ep.bias = gw.bias;
+        if (pointwise_enabled() && ep.img_Wp > 0 && pointwise_supported(srcs.data(), int(srcs.size()), gw.N, ep)) {
+            EStep sp;
+            sp.kind = EStep::PW;
+            for (size_t i = 0; i < srcs.size(); ++i) sp.pw.srcs[i] = srcs[i];
+            sp.pw.nsrc = int(srcs.size());
+            sp.pw.N = gw.N;
+            sp.pw.M = M;
+            sp.pw.W = gw.W;
+            sp.pw.ep = ep;
+            m->steps.push_back(sp);
+            return PPV_OK;
+        }
         EStep s;
         s.kind = EStep::GEMM;
         s.BN = er_pick_bn(gw.N);
@@ -543,6 +556,7 @@ int eres2net_forward(ERes2NetModel* m, const float* feat, int B, int T, float* e
                 break;
             case EStep::GEMM: rc = gemm_launch(s.gp, s.BN, m->precision, m->num_sms, st); break;
             case EStep::CONV3: rc = conv3x3_launch(s.c3, m->precision, m->num_sms, st); break;
+            case EStep::PW: rc = pointwise_launch(s.pw, m->num_sms, st); break;
             case EStep::ADD_RELU:
                 rc = launch_se_scale_res(s.a, nullptr, s.b, 0, s.d, 0, s.C, s.img_rows, s.rows, m->num_sms, st, 1, ER_RELU_MAX);
                 break;

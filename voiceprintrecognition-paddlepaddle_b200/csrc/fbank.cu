@@ -28,6 +28,7 @@ constexpr int FB_HALF = FB_NFFT / 2;  // complex FFT length
 constexpr int FB_ITEM = 16;           // frames per work item
 constexpr int FB_THREADS = 256;       // 8 warps x 2 frames
 constexpr int FB_SCR = 17 * 16;       // float2 scratch per frame: [k1][n2] padded to 17 columns
+constexpr int FB_SCR_PAIR = 2 * FB_SCR + 8;  // the two frames of a warp: the odd one starts 64 B (16 banks) past the even one's end
 constexpr int FB_MAX_MELS = 128;
 constexpr int FB_PART_ROWS = 32768;   // handle-owned partial-sum rows ([row][FB_MAX_MELS]): utterances x items per launch group
 constexpr int FB_FIN_FRAMES = 32;     // frames per finalize block
@@ -119,7 +120,7 @@ __host__ __device__ inline FbankSmem fbank_smem_layout(int nnz, int n_mels, int 
     L.mstart = take(n_mels * 4);
     L.mlen = take(n_mels * 4);
     L.moff = take(n_mels * 4);
-    L.scr = take(FB_ITEM * FB_SCR * 8 + 64);
+    L.scr = take((FB_ITEM / 2) * FB_SCR_PAIR * 8);
     L.out = take(2 * FB_ITEM * n_mels * 4);
     L.seg_stride = (((FB_ITEM - 1) * shift + win) * 4 + 127) & ~127;
     L.seg = take(2 * L.seg_stride);
@@ -190,8 +191,9 @@ __global__ void __launch_bounds__(FB_THREADS, 3)
     }
 
     const float inv_win = 1.f / float(win);
-    // the two frames of a warp sit 16 banks apart (odd slots shifted by 64 B): their 4-byte power stores / mel reads do not collide
-    float2* scr = s_scr + fl * FB_SCR + (fl & 1) * 8;
+    // the two frames of a warp sit 16 banks apart (odd slot = even slot + FB_SCR + 8 float2): their 4-byte power stores / mel reads do not
+    // collide; every pair owns its own 64 B of slack, no slot overlaps another
+    float2* scr = s_scr + (fl >> 1) * FB_SCR_PAIR + (fl & 1) * (FB_SCR + 8);
     int n = 0;
     for (int it = blockIdx.x; it < total; it += gridDim.x, ++n) {
         const int buf = n & 1;
@@ -536,7 +538,7 @@ int fbank_run(Fbank* h, const float* wav, const float* lens_ratio, int B, int L,
     const int F = h->cfg.n_mels;
     const FbankSmem lay = fbank_smem_layout(h->tb.nnz, F, h->win, h->shift);
     PPV_REQUIRE(lay.total <= 200 * 1024, "fbank_run: shared memory budget exceeded (frame shift too large)");
-    // three CTAs per SM need <= 76 800 B each (228 KB - 1 KB reserved per CTA): 76 272 B for 16 kHz / 25 ms / 10 ms / 80 bins
+    // three CTAs per SM need <= 76 800 B each (228 KB - 1 KB reserved per CTA): 76 784 B for 16 kHz / 25 ms / 10 ms / 80 bins
     const bool vec = (h->shift % 2) == 0;
     auto kern = (h->win == 400) ? (vec ? fbank_logmel_kernel<true, 400> : fbank_logmel_kernel<false, 400>)
                                 : (vec ? fbank_logmel_kernel<true, 0> : fbank_logmel_kernel<false, 0>);

@@ -86,11 +86,12 @@ __device__ __forceinline__ void epilogue_math(const Epilogue& ep, int N, int col
 }
 
 // `staging`: shared-memory address (1024-aligned) of EPI_STAGING_BYTES for the TMA-store path, 0 if unavailable.
+// `tempty_remote`: shared::cluster address of the accumulator-empty barrier when it lives in the pair leader's CTA (0: local).
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const Epilogue& ep, const CUtensorMap* map_out, int M, int N, int m0, int n0,
                                               uint32_t tmem_acc, uint32_t tfull_bar, uint32_t acc_phase, uint32_t tempty_bar, int q,
                                               int lane, int ehalf, int etid, uint32_t staging, uint8_t* staging_gen, int64_t out_row_shift = 0,
-                                              int64_t row_override = INT64_MIN, int sum_cols = 0) {
+                                              int64_t row_override = INT64_MIN, int sum_cols = 0, uint32_t tempty_remote = 0) {
     // row bookkeeping
     const int rloc = q * 32 + lane;  // row within the tile == TMEM lane
     // row_override (conv3x3.cu): the caller maps this accumulator lane to its GEMM row itself (-1: the lane holds no output)
@@ -170,7 +171,7 @@ __device__ __forceinline__ void epilogue_tile(const Epilogue& ep, const CUtensor
             }
         }
         tc_fence_before();
-        mbar_arrive(tempty_bar);
+        if (tempty_remote) mbar_arrive_cluster(tempty_remote); else mbar_arrive(tempty_bar);
         return;
     }
 
@@ -241,7 +242,7 @@ __device__ __forceinline__ void epilogue_tile(const Epilogue& ep, const CUtensor
         }
     }
     tc_fence_before();
-    mbar_arrive(tempty_bar);
+    if (tempty_remote) mbar_arrive_cluster(tempty_remote); else mbar_arrive(tempty_bar);  // pair mode: the leader CTA's barrier
 }
 
 }  // namespace ppv

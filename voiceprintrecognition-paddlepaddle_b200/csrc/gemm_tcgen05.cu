@@ -46,6 +46,11 @@ struct GemmCfg {
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES;
     static constexpr int TMEM_COLS = 2 * BN;  // 128 / 256 / 512: power of two >= 32
+    static constexpr int MAX_STAGES = 8;      // barrier slots
+    // pair mode (cta_group::2): a CTA's ring slot holds its A rows and HALF of the weight tile; the ring reuses the same bytes
+    static constexpr int PAIR_STAGE_BYTES = NA * A_BYTES + NB * (B_BYTES / 2);
+    static constexpr int PAIR_STAGES_RAW = (STAGES * STAGE_BYTES) / PAIR_STAGE_BYTES;
+    static constexpr int PAIR_STAGES = PAIR_STAGES_RAW > MAX_STAGES ? MAX_STAGES : PAIR_STAGES_RAW;
     static_assert(STAGES >= 2, "need at least a double buffer");
     static_assert(BN == 64 || BN == 128 || BN == 256, "BN");
     static_assert(BK == 64 || BK == 32, "BK");
@@ -64,7 +69,8 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
     return d;
 }
 
-template <int BN, int NSPLIT, int BK>
+// PAIR is a compile-time switch: a kernel that contains cta_group::2 instructions can only be launched in clusters of two.
+template <int BN, int NSPLIT, int BK, bool PAIR = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams gp) {
     using Cfg = GemmCfg<BN, NSPLIT, BK>;
     constexpr int STAGES = Cfg::STAGES;
@@ -76,52 +82,63 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     const uint32_t staging = smem_base + STAGES * Cfg::STAGE_BYTES;  // 1024-aligned (stage sizes are multiples of 1024)
     uint8_t* staging_gen = smem_gen + STAGES * Cfg::STAGE_BYTES;
     const uint32_t bar_base = staging + Cfg::STAGING_BYTES;
-    // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr
+    // barrier layout (8 B each): full[8], empty[8], tmem_full[2], tmem_empty[2], tmem ptr, resident-weights barrier
+    constexpr int MAXST = Cfg::MAX_STAGES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
-    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+    auto empty_bar = [&](int s) { return bar_base + 8u * (MAXST + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAXST + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MAXST + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * MAXST + 4);
     volatile uint32_t* tmem_slot_gen =
-        reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + Cfg::STAGING_BYTES + 8 * (2 * STAGES + 4));
+        reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + Cfg::STAGING_BYTES + 8 * (2 * MAXST + 4));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     // Weight-stationary mode (gp.ws, narrow convs with one n-tile and a small K): the whole weight matrix is loaded ONCE per CTA
     // into the upper half of the ring's shared memory and the ring (4 slots) carries activation tiles only -- for the
     // 32-channel 3x3 convs of the 2-D models the per-tile reload of the weights was a third of the L2 -> SM traffic.
-    const int nst = gp.ws ? GEMM_WS_STAGES : STAGES;
+    // Pair mode (gp.pair, cta_group::2): the two CTAs of a cluster own the two 128-row halves of a 256 x BN tile.  Each loads its own
+    // activation rows and HALF of the weight tile (BN / 2 rows); the leader's MMA thread issues 256 x BN x 16 MMAs that read both
+    // CTAs' shared memory and write both CTAs' TMEM.  Shared-memory fill per CTA and k-step drops from A + B to A + B / 2 (for BN = 256:
+    // 96 -> 64 KB), which is what bounds the K = 512 layers (TMA fill ~6300 B/clk chip-wide), and the ring holds more k-steps.
+    constexpr bool pair = PAIR;
+    uint32_t pair_rank = 0;
+    if constexpr (PAIR) pair_rank = cluster_ctarank();
+    const bool leader = pair_rank == 0;
+    const int stage_bytes = pair ? Cfg::PAIR_STAGE_BYTES : Cfg::STAGE_BYTES;
+    const int nst = gp.ws ? GEMM_WS_STAGES : (pair ? Cfg::PAIR_STAGES : STAGES);
     const uint32_t w_res = tiles_base + GEMM_WS_STAGES * Cfg::STAGE_BYTES;
-    const uint32_t w_full = bar_base + 8u * (2 * STAGES + 5);
+    const uint32_t w_full = bar_base + 8u * (2 * MAXST + 5);
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < GEMM_MAX_MAPS; ++i) prefetch_tmap(&gp.mapA[i]);
         prefetch_tmap(&gp.mapB);
         if (gp.epi.tma_store) prefetch_tmap(&gp.mapOut);
     }
-    // Cluster-pair mode (gp.mc): the two CTAs of a cluster work on the two m-tiles of a pair with the SAME n-tile; each loads half of
-    // every weight tile and multicasts it into both CTAs' ring slot, so a slot is free only when both CTAs' MMAs have retired
-    // (empty barriers count 2, released by multicast commits).  L2 -> SM weight traffic per CTA halves.
-    const uint32_t mc_rank = gp.mc ? cluster_ctarank() : 0u;
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), gp.mc ? 2 : 1);
+        for (int s = 0; s < MAXST; ++s) {
+            mbar_init(full_bar(s), 1);   // pair: only the leader's full barriers are used (both CTAs' loads complete_tx there)
+            mbar_init(empty_bar(s), 1);  // pair: released in both CTAs by the leader's multicast commit
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), GEMM_EPI_THREADS);
+            mbar_init(tempty_bar(a), pair ? 2 * GEMM_EPI_THREADS : GEMM_EPI_THREADS);  // pair: both CTAs' epilogues arrive at the leader
         }
         mbar_init(w_full, 1);
         fence_mbar_init();
     }
     if (warp == 2) {
-        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-        tmem_relinquish();
+        if constexpr (PAIR) {
+            tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+            tmem_relinquish_2sm();
+        } else {
+            tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
     __syncthreads();
-    if (gp.mc) cluster_sync_all();  // the peer's barriers are initialised before any multicast / remote arrive can reach them
+    if constexpr (PAIR) cluster_sync_all();  // the peer's barriers are initialised before any complete_tx / multicast commit / remote arrive can reach them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
     griddep_launch_dependents();  // PDL: the next kernel may begin its prologue
@@ -134,13 +151,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     const int num_tiles = mn_tiles * (gp.lin_splits > 0 ? gp.lin_splits : 1);
     const int nk = gp.num_ksteps;
     // work list of this CTA: tile_first, tile_first + tile_step, ... < tile_end.  Default: tile = m * n_tiles + n over all CTAs.
-    // mc: "pair tiles" pt = mp * n_tiles + n over the clusters; this CTA takes m = 2 * mp + rank (an odd last m-tile leaves one CTA of
-    // the last pair on rows >= M: it still loads and multicasts its weight halves; its loads are zero-filled and its stores dropped).
-    const int tile_first = gp.mc ? int(cluster_id_x()) : int(blockIdx.x);
-    const int tile_step = gp.mc ? int(num_clusters_x()) : int(gridDim.x);
-    const int tile_end = gp.mc ? ((gp.m_tiles + 1) / 2) * gp.n_tiles : num_tiles;
-    auto tile_m = [&](int t) { return gp.mc ? 2 * (t / gp.n_tiles) + int(mc_rank) : (t % mn_tiles) / gp.n_tiles; };
-    auto tile_n = [&](int t) { return gp.mc ? t % gp.n_tiles : (t % mn_tiles) % gp.n_tiles; };
+    // pair: "pair tiles" pt = mp * n_tiles + n over the clusters; this CTA takes m = 2 * mp + rank (an odd last m-tile leaves one CTA of
+    // the last pair on rows >= M: it still loads its weight half; its activation loads are zero-filled and its stores dropped).
+    int tile_first = int(blockIdx.x), tile_step = int(gridDim.x);
+    if constexpr (PAIR) {
+        tile_first = int(cluster_id_x());
+        tile_step = int(num_clusters_x());
+    }
+    const int tile_end = pair ? ((gp.m_tiles + 1) / 2) * gp.n_tiles : num_tiles;
+    auto tile_m = [&](int t) { return pair ? 2 * (t / gp.n_tiles) + int(pair_rank) : (t % mn_tiles) / gp.n_tiles; };
+    auto tile_n = [&](int t) { return pair ? t % gp.n_tiles : (t % mn_tiles) % gp.n_tiles; };
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -153,7 +173,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         }
         __syncwarp();
         for (int tile = tile_first; tile < tile_end; tile += tile_step) {
-            const int zsplit = gp.mc ? 0 : tile / mn_tiles;
+            const int zsplit = pair ? 0 : tile / mn_tiles;
             const int m0 = tile_m(tile) * GEMM_BM;
             const int n0 = tile_n(tile) * BN;
             // L2 prefetch of the activation rows of this CTA's NEXT tile (one CTA per m-tile issues it): they come
@@ -171,9 +191,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             for (int s = 0; s < nk; ++s) {
                 mbar_wait(empty_bar(stage), phase ^ 1u);
                 if (lane == 0) {
-                    const uint32_t sa = tiles_base + stage * Cfg::STAGE_BYTES;
+                    const uint32_t sa = tiles_base + stage * stage_bytes;
                     const uint32_t sb = sa + Cfg::NA * Cfg::A_BYTES;
                     const uint32_t fb = full_bar(stage);
+                    if constexpr (PAIR) {
+                        // both CTAs' boxes complete_tx on the LEADER's full barrier; the leader arms it with the bytes of both
+                        if (leader) mbar_arrive_expect_tx(fb, 2 * Cfg::PAIR_STAGE_BYTES);
+                        const uint32_t fbl = map_to_cta(fb, 0);
+                        const KStep ks = gp.ksteps[s];
+                        const CUtensorMap* ma = &gp.mapA[ks.map];
+#pragma unroll
+                        for (int p = 0; p < Cfg::NA; ++p) tma_load_3d_2sm(sa + p * Cfg::A_BYTES, ma, fbl, ks.a_col, m0 + ks.row_off, p);
+#pragma unroll
+                        for (int p = 0; p < Cfg::NB; ++p)
+                            tma_load_3d_2sm(sb + p * (Cfg::B_BYTES / 2), &gp.mapBh, fbl, s * BK, n0 + int(pair_rank) * (BN / 2), p);
+                    } else {
                     mbar_arrive_expect_tx(fb, gp.ws ? Cfg::NA * Cfg::A_BYTES : Cfg::STAGE_BYTES);
                     if (gp.ws) {
                         const KStep ks = gp.ksteps[s];
@@ -186,17 +218,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
 #pragma unroll
                         for (int p = 0; p < Cfg::NB; ++p)
                             tma_load_3d(sb + p * Cfg::B_BYTES, &gp.mapB, fb, kcol + gp.lin_b_col0, gp.lin_b_row0 + n0, p);
-                    } else if (gp.mc) {
-                        const KStep ks = gp.ksteps[s];
-                        const CUtensorMap* ma = &gp.mapA[ks.map];
-#pragma unroll
-                        for (int p = 0; p < Cfg::NA; ++p)
-                            tma_load_3d(sa + p * Cfg::A_BYTES, ma, fb, ks.a_col, m0 + ks.row_off, p);
-                        // this CTA's half of the weight tile (rows [rank * BN/2, +BN/2)) lands in BOTH CTAs' slot and signals both full barriers
-#pragma unroll
-                        for (int p = 0; p < Cfg::NB; ++p)
-                            tma_load_3d_mc(sb + p * Cfg::B_BYTES + mc_rank * (BN / 2) * (BK * 2), &gp.mapBh, fb, s * BK, n0 + int(mc_rank) * (BN / 2), p,
-                                           uint16_t(3));
                     } else {
                         const KStep ks = gp.ksteps[s];
                         const CUtensorMap* ma = &gp.mapA[ks.map];
@@ -207,12 +228,56 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                         for (int p = 0; p < Cfg::NB; ++p)
                             tma_load_3d(sb + p * Cfg::B_BYTES, &gp.mapB, fb, s * BK, n0, p);
                     }
+                    }
                 }
                 __syncwarp();
                 if (++stage == nst) {
                     stage = 0;
                     phase ^= 1u;
                 }
+            }
+        }
+    } else if (PAIR && warp == 1) {
+        // ===================== MMA issuer, pair mode: the leader CTA's thread drives both SMs =====================
+        if constexpr (PAIR) if (leader) {
+            constexpr uint32_t idesc2 = make_idesc_bf16(2 * GEMM_BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = tile_first; tile < tile_end; tile += tile_step) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // BOTH CTAs' epilogues drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int s = 0; s < nk; ++s) {
+                    mbar_wait(full_bar(stage), phase);  // both CTAs' operands of this k-step have landed
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t sa = tiles_base + stage * Cfg::PAIR_STAGE_BYTES;
+                        const uint32_t sb = sa + Cfg::NA * Cfg::A_BYTES;
+                        const uint64_t a_hi = make_kmajor_desc<BK>(sa);
+                        const uint64_t b_hi = make_kmajor_desc<BK>(sb);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) umma_bf16_2sm(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc2, (s > 0 || k > 0) ? 1u : 0u);
+                        if (NSPLIT == 3) {
+                            const uint64_t a_lo = make_kmajor_desc<BK>(sa + Cfg::A_BYTES);
+                            const uint64_t b_lo = make_kmajor_desc<BK>(sb + Cfg::B_BYTES / 2);
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k) umma_bf16_2sm(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc2, 1u);
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k) umma_bf16_2sm(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc2, 1u);
+                        }
+                        umma_commit_2sm(empty_bar(stage), uint16_t(3));                   // the slot is free in both CTAs
+                        if (s == nk - 1) umma_commit_2sm(tfull_bar(acc), uint16_t(3));    // both halves of the accumulator are complete
+                    }
+                    __syncwarp();
+                    if (++stage == nst) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
             }
         }
     } else if (warp == 1) {
@@ -247,11 +312,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
                     }
-                    if (gp.mc) {
-                        umma_commit_mc(empty_bar(stage), uint16_t(3));  // the slot is also the peer's multicast target
-                    } else {
-                        umma_commit(empty_bar(stage));  // smem slot free when these MMAs retire
-                    }
+                    umma_commit(empty_bar(stage));  // smem slot free when these MMAs retire
                     if (s == nk - 1) umma_commit(tfull_bar(acc));   // accumulator complete
                 }
                 __syncwarp();
@@ -274,7 +335,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             const int m0 = tile_m(tile) * GEMM_BM;
             const int n0 = tile_n(tile) * BN;
             epilogue_tile<BN>(gp.epi, &gp.mapOut, gp.M, gp.N, m0, n0, tmem_base + acc * BN, tfull_bar(acc), acc_phase, tempty_bar(acc), q,
-                              lane, ehalf, etid, staging, staging_gen, gp.mc ? 0 : int64_t(tile / mn_tiles) * gp.lin_split_rows);
+                              lane, ehalf, etid, staging, staging_gen, pair ? 0 : int64_t(tile / mn_tiles) * gp.lin_split_rows, INT64_MIN, 0,
+                              (PAIR && !leader) ? map_to_cta(tempty_bar(acc), 0) : 0u);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
         }
@@ -283,8 +345,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
 
     tc_fence_before();
     __syncthreads();
-    if (gp.mc) cluster_sync_all();  // no CTA retires while its peer may still multicast into it or arrive on its barriers
-    if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if constexpr (PAIR) cluster_sync_all();  // no CTA retires while its peer may still read its shared memory / arrive on its barriers
+    if (warp == 2) {
+        if constexpr (PAIR) {
+            tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+        } else {
+            tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -383,10 +451,11 @@ int gemm_build(GemmParams* gp, const GemmSource* srcs, int nsrc, const Planes& W
                      : 0;
     }
     {
-        // cluster-pair weight multicast: wide layers (one 256-column n-tile or more, K in the k-step table, many m-tiles) that are not weight-stationary
-        const char* mcenv = getenv("PPV_GEMM_MC");
-        gp->mc = (BN == 256 && BK == 64 && !gp->ws && gp->m_tiles >= 64 && N % BN == 0 && mcenv && mcenv[0] == '1') ? 1 : 0;
-        if (gp->mc) {
+        // pair mode (cta_group::2, 256 x 256 tiles over two SMs): wide layers with many m-tiles that are not weight-stationary.
+        // PPV_GEMM_PAIR=0 keeps them on single-CTA 128 x 256 tiles (A-B timing).
+        const char* penv = getenv("PPV_GEMM_PAIR");
+        gp->pair = (BN == 256 && !gp->ws && gp->m_tiles >= 64 && N % BN == 0 && !(penv && penv[0] == '0')) ? 1 : 0;
+        if (gp->pair) {
             rc = encode_planes_map_ex(&gp->mapBh, W, BK, BN / 2, BK * 2);
             if (rc) return rc;
         }
@@ -469,7 +538,9 @@ static int launch_one(const GemmParams& gp, int num_sms, cudaStream_t stream) {
     PPV_ONCE_PER_DEVICE(PPV_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, NSPLIT, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES)));
     const int tiles = gp.m_tiles * gp.n_tiles * (gp.lin_splits > 0 ? gp.lin_splits : 1);
-    if (gp.mc) {  // clusters of two CTAs; one cluster per pair tile at most
+    if constexpr (BN == 256) if (gp.pair) {  // clusters of two CTAs; one cluster per pair tile at most
+        PPV_ONCE_PER_DEVICE(PPV_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, NSPLIT, BK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg::SMEM_BYTES)));
         const int pair_tiles = ((gp.m_tiles + 1) / 2) * gp.n_tiles;
         const int clusters = std::min(pair_tiles, num_sms / 2);
         cudaLaunchConfig_t cfg = {};
@@ -486,7 +557,7 @@ static int launch_one(const GemmParams& gp, int num_sms, cudaStream_t stream) {
         attr[1].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 2;
-        PPV_PDL_OK(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, NSPLIT, BK>, gp), "gemm_tcgen05_kernel (cluster pairs)");
+        PPV_PDL_OK(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, NSPLIT, BK, true>, gp), "gemm_tcgen05_kernel (cta_group::2 pairs)");
         return PPV_OK;
     }
     const int grid = std::min(tiles, num_sms);

@@ -34,7 +34,8 @@ struct BlockW {
 };
 
 struct RStep {
-    enum Kind { CONV1, GEMM, CONV3, POOL, SCALE_RES, FLATTEN, ASP_GLOBAL, ASP_FUSED } kind;
+    enum Kind { CONV1, GEMM, CONV3, PW, POOL, SCALE_RES, FLATTEN, ASP_GLOBAL, ASP_FUSED } kind;
+    PwStep pw;  // PW: 1x1 conv with K <= 64 on the CUDA cores (pointwise.cu)
     Conv3x3Params c3;  // CONV3: 3x3 conv with 32 -> 32 channels (layer1), conv3x3.cu
     GemmParams gp;
     AspFusedParams ap;
@@ -681,6 +682,7 @@ int resnetse_forward(ResNetSEModel* m, const float* feat, int B, int T, float* e
             }
             case RStep::GEMM: rc = gemm_launch(s.gp, s.BN, m->precision, m->num_sms, st); break;
             case RStep::CONV3: rc = conv3x3_launch(s.c3, m->precision, m->num_sms, st); break;
+            case RStep::PW: rc = pointwise_launch(s.pw, m->num_sms, st); break;
             case RStep::POOL:
                 rc = launch_colstats(s.a, 0, s.C, B, s.img_rows, 0, s.img_rows, 0, 0.f, nullptr, s.b, st, s.inv_count);
                 break;
