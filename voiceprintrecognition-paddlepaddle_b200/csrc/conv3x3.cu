@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv3x3_c32_kernel(const __gr
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), GEMM_EPI_THREADS / 2);  // one epilogue warp group (4 warps) per accumulator
+            mbar_init(tempty_bar(a), EPI_WARP_ARRIVALS / 2);  // one epilogue warp group (4 warps) per accumulator, one arrival per warp
         }
         mbar_init(w_full, 1);
         fence_mbar_init();

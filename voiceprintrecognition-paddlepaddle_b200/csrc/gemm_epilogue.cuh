@@ -11,7 +11,8 @@ namespace ppv {
 constexpr int GEMM_EPI_THREADS = 256;                 // 8 epilogue warps
 constexpr int GEMM_THREADS = 128 + GEMM_EPI_THREADS;  // + TMA, MMA, TMEM-alloc, spare warps
 
-constexpr int EPI_STAGING_BYTES = 2 * GEMM_BM * 128;  // [hi | lo] x 128 rows x 64 bf16 columns, SWIZZLE_128B
+constexpr int EPI_STAGING_BYTES = 2 * GEMM_BM * 128;
+constexpr int EPI_WARP_ARRIVALS = GEMM_EPI_THREADS / 32;  // accumulator-empty barrier: ONE arrival per epilogue warp (lane 0, after its last TMEM read)  // [hi | lo] x 128 rows x 64 bf16 columns, SWIZZLE_128B
 
 // per-column epilogue math on 32 accumulator columns starting at global column `col`
 __device__ __forceinline__ void epilogue_math(const Epilogue& ep, int N, int col, int64_t grp, int64_t sgrp, const uint32_t (&v)[32],
@@ -126,9 +127,14 @@ __device__ __forceinline__ void epilogue_tile(const Epilogue& ep, const CUtensor
     const uint32_t t_addr = tmem_acc + (uint32_t(q * 32) << 16);
 
     if (ep.tma_store && staging != 0) {
-        // ---- planes output without halo: 64-column slabs through a swizzled staging tile, written out by TMA with full
-        // 128-byte lines.  Garbage rows (time padding, rows >= M) are stored too: their consumers never read them.
+        // ---- planes output without halo: each half of the epilogue (ehalf: four warps = the 128 rows of the tile) streams ITS 32-column
+        // chunks through its own swizzled staging tile ([hi | lo] x 128 rows x 64 B, SWIZZLE_64B) and writes them out by TMA; the two halves
+        // share nothing (own named barrier, own bulk groups), so one half's store drain / barrier wait overlaps the other's math.
+        // Garbage rows (time padding, rows >= M) are stored too: their consumers never read them.
         const int64_t gsafe = valid ? grp : 0;
+        const uint32_t stg = staging + ehalf * (EPI_STAGING_BYTES / 2);
+        uint8_t* sh = staging_gen + ehalf * (EPI_STAGING_BYTES / 2) + rloc * 64;
+        const bool issuer = (etid & 127) == 0;
 #pragma unroll 1
         for (int s = 0; s < BN / 64; ++s) {
             const int c = 2 * s + ehalf;
@@ -137,6 +143,13 @@ __device__ __forceinline__ void epilogue_tile(const Epilogue& ep, const CUtensor
             __syncwarp();
             tmem_ld32(t_addr + c * 32, v);
             tmem_ld_wait();
+            if (s == BN / 64 - 1) {  // this warp's last read of the accumulator: hand it back before the math / staging / store of the chunk
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (tempty_remote) mbar_arrive_cluster(tempty_remote); else mbar_arrive(tempty_bar);
+                }
+            }
             float x[32];
             if (col < N && (valid || !ep.zero_invalid)) {
                 epilogue_math(ep, N, col, gsafe, sgrp, v, x);
@@ -144,34 +157,25 @@ __device__ __forceinline__ void epilogue_tile(const Epilogue& ep, const CUtensor
 #pragma unroll
                 for (int j = 0; j < 32; ++j) x[j] = 0.f;
             }
-            if (etid == 0) bulk_wait_read0();  // the previous slab's TMA stores have drained the staging tile
-            named_bar_sync(1, GEMM_EPI_THREADS);
-            uint8_t* sh = staging_gen + rloc * 128;
+            uint32_t hw[16], lw[16];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {  // four 16-byte chunks (8 columns each) of this thread's 32 columns
-                uint32_t hw[4], lw[4];
+            for (int j = 0; j < 16; ++j) split_pack_bf16x2(x[2 * j], x[2 * j + 1], hw[j], lw[j]);
+            if (issuer) bulk_wait_read0();  // this half's previous stores have drained its staging tile
+            named_bar_sync(1 + ehalf, GEMM_EPI_THREADS / 2);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    __nv_bfloat16 h0, l0, h1, l1;
-                    split_bf16(x[8 * k + 2 * j], h0, l0);
-                    split_bf16(x[8 * k + 2 * j + 1], h1, l1);
-                    hw[j] = pack_bf16x2(h0, h1);
-                    lw[j] = pack_bf16x2(l0, l1);
-                }
-                const int chunk = ((ehalf * 4 + k) ^ (rloc & 7)) << 4;  // SWIZZLE_128B: 16-byte chunk index XOR (row mod 8)
-                *reinterpret_cast<uint4*>(sh + chunk) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                *reinterpret_cast<uint4*>(sh + GEMM_BM * 128 + chunk) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            for (int k = 0; k < 4; ++k) {  // four 16-byte chunks (8 columns each); SWIZZLE_64B: chunk index XOR ((row >> 1) & 3)
+                const int chunk = (k ^ ((rloc >> 1) & 3)) << 4;
+                *reinterpret_cast<uint4*>(sh + chunk) = make_uint4(hw[4 * k], hw[4 * k + 1], hw[4 * k + 2], hw[4 * k + 3]);
+                *reinterpret_cast<uint4*>(sh + GEMM_BM * 64 + chunk) = make_uint4(lw[4 * k], lw[4 * k + 1], lw[4 * k + 2], lw[4 * k + 3]);
             }
             fence_proxy_async_smem();
-            named_bar_sync(1, GEMM_EPI_THREADS);
-            if (etid == 0 && n0 + s * 64 < N && !ep.debug_nostore) {
-                tma_store_3d(map_out, staging, ep.out_col0 + n0 + s * 64, m0, 0);
-                tma_store_3d(map_out, staging + GEMM_BM * 128, ep.out_col0 + n0 + s * 64, m0, 1);
+            named_bar_sync(1 + ehalf, GEMM_EPI_THREADS / 2);
+            if (issuer && col < N && !ep.debug_nostore) {
+                tma_store_3d(map_out, stg, ep.out_col0 + col, m0, 0);
+                tma_store_3d(map_out, stg + GEMM_BM * 64, ep.out_col0 + col, m0, 1);
                 bulk_commit_group();
             }
         }
-        tc_fence_before();
-        if (tempty_remote) mbar_arrive_cluster(tempty_remote); else mbar_arrive(tempty_bar);
         return;
     }
 
@@ -217,13 +221,7 @@ __device__ __forceinline__ void epilogue_tile(const Epilogue& ep, const CUtensor
         } else {
             uint32_t h[16], l[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                __nv_bfloat16 h0, l0, h1, l1;
-                split_bf16(x[2 * j], h0, l0);
-                split_bf16(x[2 * j + 1], h1, l1);
-                h[j] = pack_bf16x2(h0, h1);
-                l[j] = pack_bf16x2(l0, l1);
-            }
+            for (int j = 0; j < 16; ++j) split_pack_bf16x2(x[2 * j], x[2 * j + 1], h[j], l[j]);
             __nv_bfloat16* obase = static_cast<__nv_bfloat16*>(ep.out) + ep.out_col0 + col;
             auto store_row = [&](int64_t r) {  // 64 B per plane = two full 32-byte sectors
                 __nv_bfloat16* ph = obase + r * ep.out_ld;
@@ -242,7 +240,10 @@ __device__ __forceinline__ void epilogue_tile(const Epilogue& ep, const CUtensor
         }
     }
     tc_fence_before();
-    if (tempty_remote) mbar_arrive_cluster(tempty_remote); else mbar_arrive(tempty_bar);  // pair mode: the leader CTA's barrier
+    __syncwarp();
+    if (lane == 0) {
+        if (tempty_remote) mbar_arrive_cluster(tempty_remote); else mbar_arrive(tempty_bar);  // pair mode: the leader CTA's barrier
+    }
 }
 
 }  // namespace ppv

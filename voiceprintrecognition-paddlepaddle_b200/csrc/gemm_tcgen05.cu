@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), pair ? 2 * GEMM_EPI_THREADS : GEMM_EPI_THREADS);  // pair: both CTAs' epilogues arrive at the leader
+            mbar_init(tempty_bar(a), pair ? 2 * EPI_WARP_ARRIVALS : EPI_WARP_ARRIVALS);  // one arrival per epilogue warp; pair: both CTAs' warps arrive at the leader
         }
         mbar_init(w_full, 1);
         fence_mbar_init();
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
         }
-        if (etid == 0) bulk_wait_all();  // TMA stores issued by this thread have completed before the CTA retires
+        if ((etid & 127) == 0) bulk_wait_all();  // TMA stores issued by the two issuing threads have completed before the CTA retires
     }
 
     tc_fence_before();
@@ -478,7 +478,7 @@ int gemm_build(GemmParams* gp, const GemmSource* srcs, int nsrc, const Planes& W
             po.plane_stride = epi.out_plane_stride;
             po.rows = epi.out_plane_stride / epi.out_ld;  // planes are allocated back to back
             if (po.rows * po.ld == po.plane_stride && (epi.out_col0 % 8) == 0) {
-                rc = encode_planes_map_ex(&gp->mapOut, po, 64, GEMM_BM, 128);
+                rc = encode_planes_map_ex(&gp->mapOut, po, 32, GEMM_BM, 64);  // 32-column chunks, SWIZZLE_64B staging (gemm_epilogue.cuh)
                 if (rc) return rc;
                 gp->epi.tma_store = 1;
                 if (img_same_grid) gp->epi.zero_invalid = 1;

@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(256, 2) pw_conv_kernel(const PwParams p) {
 }  // namespace
 
 // A 1x1 conv qualifies when every source is a 32- or 64-column window at row offset 0, the total K is 32 or 64, N is a multiple of 32
-// (K N <= 4096), the output goes to split planes (plain rows or an image grid, any stride) and the epilogue is bias (+ ReLU / clipped ReLU).
+// (<= 64; the selection rule below keeps K = 32 only), the output goes to split planes (plain rows or an image grid, any stride) and the epilogue is bias (+ ReLU / clipped ReLU).
 bool pointwise_supported(const GemmSource* srcs, int nsrc, int N, const Epilogue& ep) {
     if (nsrc < 1 || nsrc > 2 || N % 32 != 0 || N > 128) return false;
     int K = 0;
@@ -136,8 +136,10 @@ bool pointwise_supported(const GemmSource* srcs, int nsrc, int N, const Epilogue
         if (nsrc == 2 && srcs[i].ncols != 32) return false;  // two sources: 32 + 32
         K += srcs[i].ncols;
     }
-    if (K != 32 && K != 64) return false;
-    if (K * N > 4096) return false;  // 2 K N FLOP per position on the FMA pipe: beyond 64 x 64 the tensor path is faster
+    // Measured at 80 x 298 x 256 positions (profiles/eres2net_launches_r2_summary.txt): K = 32 -> 870 us against 950 us on the gather-GEMM, but
+    // K = 64 -> 1670 us against 1020 us: every 4 FMAs cost one broadcast LDS.128 (4 LSU cycles per warp), so the kernel is shared-memory
+    // bound at 4x its FMA time.  Only the K = 32 layers are routed here.
+    if (K != 32 || N > 64) return false;
     if (ep.out_mode != OUT_PLANES || ep.rowgrp_bias || ep.seg_scale || ep.bn_scale || ep.tanh_ || ep.sigmoid_ || ep.silu_ || ep.Tp != 0 || ep.halo) return false;
     return (ep.out_ld % 16) == 0 && (ep.out_col0 % 16) == 0 && (ep.out_plane_stride % 16) == 0;
 }

@@ -128,7 +128,9 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank
 }
 // arrive on an mbarrier of another CTA of the cluster (address from map_to_cta)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+    // default semantics (release at CTA scope), as cutlass::arch::ClusterBarrier::arrive(cta_id): the accumulator hand-over is ordered by the
+    // tcgen05 fences; a cluster-scope release would put a MEMBAR.ALL.GPU in front of every arrive
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -282,9 +284,12 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 // fp32 -> (hi, lo) bf16 split: hi = rn(x), lo = rn(x - hi).  x ~= hi + lo to ~2^-17 relative.
+// The scalar cvt.rn.bf16.f32 compiles to F2F.BF16.F32 (conversion pipe, 16 lanes / clk / SM); the packed cvt.rn.bf16x2.f32 compiles to
+// F2FP.BF16.F32.PACK_AB (ALU, full rate).  Same round-to-nearest-even result: a lone value converts through the packed form with a zero.
+__device__ __forceinline__ __nv_bfloat16 bf16_rn_fast(float x) { return __low2bfloat16(__floats2bfloat162_rn(x, 0.f)); }
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-    hi = __float2bfloat16_rn(x);
-    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+    hi = bf16_rn_fast(x);
+    lo = bf16_rn_fast(x - __bfloat162float(hi));
 }
 // (a, b) -> packed hi = {bf16(a) | bf16(b) << 16} and lo = the same for the residuals; one F2FP per pack
 __device__ __forceinline__ void split_pack_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {

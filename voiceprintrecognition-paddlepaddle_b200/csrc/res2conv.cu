@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) res2conv_kernel(const __grid_
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), GEMM_EPI_THREADS);
+            mbar_init(tempty_bar(a), EPI_WARP_ARRIVALS);
         }
         mbar_init(w_full, 1);
         fence_mbar_init();
