@@ -1,13 +1,13 @@
-// 1x1 convolutions with a tiny contraction (K <= 64 input channels, one or two 32 / 64-channel sources) over image grids or plain row
-// ranges: the bottleneck convs of ResNetSE's first stage (ppvector/models/resnet_se.py:24-45: conv1 32/64 -> 32, conv3 32 -> 64, the 1x1
-// downsample), ERes2Net's conv1 / conv3 / shortcut of layers 1-2 (ppvector/models/eres2net.py:85-108) and CAM++'s FCM shortcuts
-// (ppvector/models/campplus.py:232-238).
+// 1x1 convolutions with K = 32 input channels (one 32-channel source) and N <= 64 output channels over image grids or plain row ranges:
+// ResNetSE's first-stage conv1 / conv3 / downsample where the input is the 32-channel stem (ppvector/models/resnet_se.py:24-45),
+// ERes2Net's layer-1 conv1 / shortcut (ppvector/models/eres2net.py:85-108) and CAM++'s FCM shortcuts (ppvector/models/campplus.py:232-238).
 //
-// On the tcgen05 gather-GEMM these layers run one 128-row tile per pipeline step with a single 32- or 64-wide k-step: 49 200 tiles of
-// 16 KB each at the 80 x 298 resolution, paced by the per-tile barrier round trips (measured 856-1020 us per launch against a
-// ~300 us HBM floor: profiles/{resnetse,eres2net}_launches_r2_summary.txt).  With K <= 64 there is nothing for a tensor core to amortise:
-// here one thread owns one grid position, keeps its K input values (exact hi + lo) in registers, and walks the fp32 weight matrix in
-// shared memory with broadcast 16-byte loads -- 2 K N FLOP per position on the FMA pipe, HBM-bound.
+// On the tcgen05 gather-GEMM these layers run one 128-row tile per pipeline step with a single 32-wide k-step: 49 200 tiles of 16 KB at
+// the 80 x 298 resolution, paced by the per-tile epilogue chain (~950 us per launch against a ~300 us HBM floor:
+// profiles/eres2net_launches_r2_summary.txt).  Here one thread owns one grid position, keeps its 32 input values (exact hi + lo) in
+// registers and walks the fp32 weight matrix in shared memory with broadcast 16-byte loads: 2 K N FLOP per position on the FMA pipe.
+// Measured 870 us at K = 32; the same kernel at K = 64 took 1670 us (every 4 FMAs cost one broadcast LDS.128 = 4 LSU cycles per warp, i.e.
+// shared-memory bound at 4x its FMA time) against 1020 us on the tensor path, so only K = 32 is routed here.
 #include <type_traits>
 
 #include "common.h"
@@ -17,7 +17,6 @@ namespace ppv {
 
 namespace {
 
-constexpr int PW_MAXK = 64;
 constexpr int PW_NCH = 32;  // output channels per accumulator pass
 
 struct PwParams {
@@ -73,12 +72,7 @@ __global__ void __launch_bounds__(256, 2) pw_conv_kernel(const PwParams p) {
                 }
             }
         };
-        if (p.nsrc == 1) {
-            load(p.src[0], p.col0[0], std::integral_constant<int, K>{}, x);
-        } else {  // two 32-channel sources (K = 64): concat order = source order
-            load(p.src[0], p.col0[0], std::integral_constant<int, K / 2>{}, x);
-            load(p.src[1], p.col0[1], std::integral_constant<int, K / 2>{}, x + K / 2);
-        }
+        load(p.src[0], p.col0[0], std::integral_constant<int, K>{}, x);
         // ---- PW_NCH output channels at a time ----
         for (int n0 = 0; n0 < N; n0 += PW_NCH) {
             float acc[PW_NCH];
@@ -126,20 +120,11 @@ __global__ void __launch_bounds__(256, 2) pw_conv_kernel(const PwParams p) {
 
 }  // namespace
 
-// A 1x1 conv qualifies when every source is a 32- or 64-column window at row offset 0, the total K is 32 or 64, N is a multiple of 32
-// (<= 64; the selection rule below keeps K = 32 only), the output goes to split planes (plain rows or an image grid, any stride) and the epilogue is bias (+ ReLU / clipped ReLU).
+// A 1x1 conv qualifies when its single source is a 32-column window at row offset 0, N is 32 or 64, the output goes to split planes (plain
+// rows or an image grid, any stride) and the epilogue is bias (+ ReLU / clipped ReLU).
 bool pointwise_supported(const GemmSource* srcs, int nsrc, int N, const Epilogue& ep) {
-    if (nsrc < 1 || nsrc > 2 || N % 32 != 0 || N > 128) return false;
-    int K = 0;
-    for (int i = 0; i < nsrc; ++i) {
-        if (srcs[i].row_off != 0 || (srcs[i].ncols != 32 && srcs[i].ncols != 64) || srcs[i].col0 % 8 != 0 || srcs[i].t.ld % 8 != 0) return false;
-        if (nsrc == 2 && srcs[i].ncols != 32) return false;  // two sources: 32 + 32
-        K += srcs[i].ncols;
-    }
-    // Measured at 80 x 298 x 256 positions (profiles/eres2net_launches_r2_summary.txt): K = 32 -> 870 us against 950 us on the gather-GEMM, but
-    // K = 64 -> 1670 us against 1020 us: every 4 FMAs cost one broadcast LDS.128 (4 LSU cycles per warp), so the kernel is shared-memory
-    // bound at 4x its FMA time.  Only the K = 32 layers are routed here.
-    if (K != 32 || N > 64) return false;
+    if (nsrc != 1 || N % 32 != 0 || N > 64) return false;
+    if (srcs[0].row_off != 0 || srcs[0].ncols != 32 || srcs[0].col0 % 8 != 0 || srcs[0].t.ld % 8 != 0) return false;
     if (ep.out_mode != OUT_PLANES || ep.rowgrp_bias || ep.seg_scale || ep.bn_scale || ep.tanh_ || ep.sigmoid_ || ep.silu_ || ep.Tp != 0 || ep.halo) return false;
     return (ep.out_ld % 16) == 0 && (ep.out_col0 % 16) == 0 && (ep.out_plane_stride % 16) == 0;
 }
@@ -162,11 +147,7 @@ int pointwise_launch(const GemmSource* srcs, int nsrc, const Planes& W, int64_t 
     p.ep = ep;
     const size_t smem = size_t(p.K) * N * sizeof(float);
     const int grid = int(std::min<int64_t>((M + 255) / 256, int64_t(num_sms) * 8));
-    if (p.K == 32) {
-        PPV_PDL_OK(launch_pdl(pw_conv_kernel<32>, dim3(grid), dim3(256), smem, st, p), "pw_conv_kernel<32>");
-    } else {
-        PPV_PDL_OK(launch_pdl(pw_conv_kernel<64>, dim3(grid), dim3(256), smem, st, p), "pw_conv_kernel<64>");
-    }
+    PPV_PDL_OK(launch_pdl(pw_conv_kernel<32>, dim3(grid), dim3(256), smem, st, p), "pw_conv_kernel<32>");
     return PPV_OK;
 }
 
