@@ -239,6 +239,11 @@ int64_t ppv_trainer_param_count(const ppv_trainer_t* h); /* floats in the parame
 int64_t ppv_trainer_stat_count(const ppv_trainer_t* h);  /* floats in the running-statistics buffer */
 int ppv_trainer_lookup(const ppv_trainer_t* h, const char* name, int64_t* offset, int64_t* numel, int* is_stat);
 int ppv_trainer_bind(ppv_trainer_t* h, float* params, float* grads, float* stats);
+/* Operand precision of the step's GEMMs (forward, data gradients, weight gradients): PPV_PREC_BF16X3 (default, fp32-grade) or
+ * PPV_PREC_BF16 -- the B200 form of train_conf.enable_amp (ppvector/trainer.py:167, 209-229: paddle.amp.auto_cast level O1 + GradScaler
+ * around the same step): single-pass bf16 operands, fp32 accumulation, fp32 BatchNorm / pooling / loss / master weights / Adam; bf16
+ * keeps fp32's exponent range, so there is no loss scaling. */
+int ppv_trainer_set_precision(ppv_trainer_t* h, int precision);
 size_t ppv_trainer_workspace_bytes(ppv_trainer_t* h, int B, int T);
 /* feat [B,T,F] fp32, labels [B] int64 (device).  Overwrites the whole gradient buffer with d(loss)/d(param), updates the
  * running statistics, writes the scalar loss and (optionally) the cosine logits [B, num_classes] (device pointers). */

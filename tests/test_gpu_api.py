@@ -220,3 +220,22 @@ def test_trainer_train_runs_the_cuda_step(cuda, wavs, cfg, tmp_path):
     cfg2["model_conf"]["model"] = "ResNetSE"
     with pytest.raises(NotImplementedError):
         PPVectorTrainer(cfg2, use_gpu=True).train()
+
+
+@pytest.mark.parametrize("lanes", [1, 2, 3])
+def test_streaming_lanes_equal_the_single_call(cuda, cfg, W64, lanes):
+    """extract_embeddings_stream / embed_resident_stream keep `lanes` batches in the kernels at once (replica models on their own streams):
+    every batch must come back in order and bitwise equal to the one-batch-at-a-time call, for more batches than lanes and staging buffers."""
+    pred = PPVectorPredictor(cfg, model_path=None, use_gpu=True, state_dict={k: v.float().numpy() for k, v in W64.items()})
+    g = torch.Generator().manual_seed(31)
+    host = [(0.1 * torch.randn(5, 16000, generator=g)).pin_memory() for i in range(7)]
+    want = [pred.extract_embeddings(h.numpy()) for h in host]
+    got = [out.numpy().copy() for out in pred.extract_embeddings_stream(iter(host), lanes=lanes)]
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    dev = [h.to(cuda) for h in host]
+    outs = pred.embed_resident_stream(dev, lanes=lanes)
+    torch.cuda.synchronize()
+    for a, b in zip(outs, want):
+        assert np.array_equal(a.cpu().numpy(), b)

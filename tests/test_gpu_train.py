@@ -143,3 +143,60 @@ def test_gradients_at_the_config_size(cuda, W64):
             bad.append((name, rel, cos))
     print("worst relative gradient error per group at 64 x 298:", {k: f"{v:.2e}" for k, v in worst.items()})
     assert not bad, (bad[:10], worst)
+
+
+def test_amp_bf16_operands_track_the_fp64_oracle(cuda, W64):
+    """train_conf.enable_amp (reference trainer.py:167, 209-229: auto_cast O1 + GradScaler) runs here as single-pass bf16 GEMM operands with
+    fp32 accumulation and fp32 BatchNorm / pooling / loss / Adam.  Each product carries 2^-9 relative rounding per operand, so the step is
+    compared with the fp64 oracle at the precision class the reference's fp16 autocast trains at -- tolerances stated below are ~2x what
+    was measured (printed with -s): loss within 5e-3 relative; the head (classifier / fc / asp_bn) within 5e-2 (measured 2.2e-2); weight
+    matrices cosine > 0.96, relative L2 error < 0.3; per-channel vectors (64-element conv biases and BatchNorm affine gradients, sums that
+    cancel) cosine > 0.85, relative error < 0.6 (measured worst 0.948 / 0.32).  A short Adam run must follow the oracle's loss curve within 3e-2."""
+    B, T = 4, 40
+    f, y, Wc = make_problem(B, T, 140)
+    loss, grads, stats, logits = ot.train_step_grads(f, y, W64, Wc, margin=0.2, label_smoothing=0.0)
+    eng = new_engine(cuda, W64, Wc)
+    eng.set_precision("bf16")
+    got_loss = eng.forward_backward(f.float().to(cuda), y.to(cuda), margin=0.2)
+    torch.cuda.synchronize()
+    lrel = abs(got_loss.item() - loss.item()) / abs(loss.item())
+    worst = {"w_rel": (0.0, ""), "w_cos": (1.0, ""), "v_rel": (0.0, ""), "v_cos": (1.0, ""), "head": (0.0, "")}
+    for name, gw in grads.items():
+        if name == "asp.conv.conv.bias":
+            continue
+        gg = eng.view(name, tuple(gw.shape), "grad").double().cpu()
+        rel = ((gg - gw).norm() / (gw.norm() + 1e-12)).item()
+        cos = ((gg * gw).sum() / (gg.norm() * gw.norm() + 1e-30)).item()
+        if name.startswith(("classifier", "fc.", "asp_bn.")):
+            worst["head"] = max(worst["head"], (rel, name))
+        k = "w" if gw.dim() >= 2 else "v"  # weight matrices / per-channel vectors (biases, BatchNorm affine: sums that cancel)
+        worst[k + "_rel"] = max(worst[k + "_rel"], (rel, name))
+        worst[k + "_cos"] = min(worst[k + "_cos"], (cos, name))
+    print("amp bf16: loss rel", lrel, "worst", worst)
+    assert lrel < 5e-3, lrel
+    assert worst["head"][0] < 5e-2, worst
+    assert worst["w_rel"][0] < 0.3 and worst["w_cos"][0] > 0.96, worst
+    assert worst["v_rel"][0] < 0.6 and worst["v_cos"][0] > 0.85, worst
+    # the split-bf16 default really is a different (tighter) path
+    eng3 = new_engine(cuda, W64, Wc)
+    l3 = eng3.forward_backward(f.float().to(cuda), y.to(cuda), margin=0.2)
+    assert abs(l3.item() - loss.item()) < abs(got_loss.item() - loss.item()) + 1e-7
+
+    steps = 6
+    fs, ys = [], []
+    for i in range(steps):
+        fi, yi, _ = make_problem(4, 33, 500 + i)
+        fs.append(fi)
+        ys.append(yi)
+    _, _, Wc0 = make_problem(4, 33, 500)
+    margins = [ot.margin_at(i, 1, 5, 0.0, 0.3) for i in range(steps)]
+    want, _, _ = ot.train_loop(fs, ys, W64, Wc0, lr=1e-4, weight_decay=1e-6, margins=margins)
+    eng = new_engine(cuda, W64, Wc0)
+    eng.set_precision("bf16")
+    got = []
+    for i in range(steps):
+        li = eng.forward_backward(fs[i].float().to(cuda), ys[i].to(cuda), margin=margins[i])
+        eng.adam_step(lr=1e-4, weight_decay=1e-6, grad_scale=eng.all_reduce_grads())
+        got.append(li.item())
+    print("amp bf16 loss curve", got, want)
+    assert np.allclose(got, want, rtol=3e-2), (got, want)

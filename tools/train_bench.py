@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--speakers", type=int, default=2796)
     ap.add_argument("--once", action="store_true")
+    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"], help="bf16 = train_conf.enable_amp")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -33,6 +34,7 @@ def main():
     dev = torch.device("cuda", local)
     torch.manual_seed(1000)
     eng = TrainEngine(input_size=80, num_speakers=a.speakers, device=dev)
+    eng.set_precision(a.precision)
     eng.load_state_dict(EcapaTdnn(input_size=80).state_dict(), torch.nn.init.xavier_uniform_(torch.empty(192, a.speakers)))
     g = torch.Generator().manual_seed(1000 + rank)
     x = torch.randn(a.batch, a.frames, 80, generator=g)
@@ -85,7 +87,7 @@ def main():
         ms = float(t.item())
     if rank == 0:
         # algorithmic work: training step ~ 3 x forward, forward 2.857 GFLOP / utterance as executed
-        print(json.dumps({"metric": "train_samples_per_s", "value": round(world * a.batch / ms * 1e3, 1), "n_gpus": world, "ms_per_step": round(ms, 3),
+        print(json.dumps({"metric": "train_samples_per_s", "value": round(world * a.batch / ms * 1e3, 1), "n_gpus": world, "precision": a.precision, "ms_per_step": round(ms, 3),
                           "batch_per_gpu": a.batch, "frames": a.frames, "speakers": a.speakers, "loss": float(loss),
                           "algorithmic_tflops": round(world * a.batch * 3 * 2.857e9 / (ms * 1e-3) / 1e12, 1),
                           "workspace_GB": round(eng._ws.numel() / 2**30, 2),

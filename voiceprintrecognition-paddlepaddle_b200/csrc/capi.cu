@@ -385,6 +385,12 @@ int ppv_trainer_lookup(const ppv_trainer_t* h, const char* name, int64_t* offset
     return trainer_lookup(h->impl, name, offset, numel, is_stat);
     PPV_GUARD_END
 }
+int ppv_trainer_set_precision(ppv_trainer_t* h, int precision) {
+    PPV_GUARD_BEGIN
+    PPV_REQUIRE(h, "ppv_trainer_set_precision: null handle");
+    return trainer_set_precision(h->impl, precision);
+    PPV_GUARD_END
+}
 int ppv_trainer_bind(ppv_trainer_t* h, float* params, float* grads, float* stats) {
     PPV_GUARD_BEGIN
     PPV_REQUIRE(h, "ppv_trainer_bind: null handle");

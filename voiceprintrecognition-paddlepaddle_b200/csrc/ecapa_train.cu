@@ -84,6 +84,7 @@ struct Trainer {
     int S = 0;  // classes
     int C = 0, C3 = 0, width = 0, scale = 0, Fp = 0, P = 0, att = 0, se = 0, D = 0;
     int num_sms = 148;
+    int precision = PPV_PREC_BF16X3;  // PPV_PREC_BF16: single-pass bf16 operands for every forward / data-gradient / weight-gradient GEMM (AMP mode)
     // flat layout
     std::map<std::string, std::pair<int64_t, int64_t>> pmap, smap;  // name -> (offset, numel)
     int64_t n_params = 0, n_stats = 0;
@@ -221,6 +222,13 @@ int trainer_lookup(const Trainer* t, const char* name, int64_t* off, int64_t* nu
     }
     return fail(PPV_EINVAL, std::string("trainer_lookup: unknown tensor ") + name);
 }
+int trainer_set_precision(Trainer* t, int precision) {
+    PPV_REQUIRE(t, "trainer_set_precision: null handle");
+    PPV_REQUIRE(precision == PPV_PREC_BF16X3 || precision == PPV_PREC_BF16, "trainer_set_precision: PPV_PREC_BF16X3 or PPV_PREC_BF16");
+    t->precision = precision;
+    return PPV_OK;
+}
+
 int trainer_bind(Trainer* t, float* params, float* grads, float* stats) {
     PPV_REQUIRE(t && params && grads && stats, "trainer_bind: null argument");
     PPV_REQUIRE(((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(stats)) & 31) == 0,
@@ -729,7 +737,7 @@ int trainer_forward_backward(Trainer* t, const float* feat, const int64_t* label
                 break;
             }
             case TStep::PACK: rc = launch_pack_features(feat, B, T, t->cfg.input_size, t->X0, P, Tp, st); break;
-            case TStep::GEMM: rc = gemm_launch(s.gp, s.BN, PPV_PREC_BF16X3, t->num_sms, st); break;
+            case TStep::GEMM: rc = gemm_launch(s.gp, s.BN, t->precision, t->num_sms, st); break;
             case TStep::BN_FWD: {
                 const TBN& bn = t->L[s.layer].bn;
                 rc = tr_bn_forward(s.p0, s.c0, bn.C, B, T, P, Tp, TR_BN_EPS, TR_BN_MOMENTUM, par + bn.g_off, par + bn.b_off, bn.mean, bn.rstd, bn.scale,
@@ -831,7 +839,7 @@ int trainer_forward_backward(Trainer* t, const float* feat, const int64_t* label
                     if (rc) return rc;
                 }
                 for (const GemmParams& gp : s.wg) {
-                    rc = gemm_launch(gp, s.BN, PPV_PREC_BF16X3, t->num_sms, st);
+                    rc = gemm_launch(gp, s.BN, t->precision, t->num_sms, st);
                     if (rc) return rc;
                 }
                 rc = tr_wgrad_unpack(t->wpart, s.a, s.b, c.Cout, c.Cin, c.Cinp, c.taps, grd + c.w_off, int64_t(c.CinTotal) * c.taps, st);

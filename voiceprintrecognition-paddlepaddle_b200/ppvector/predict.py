@@ -104,52 +104,114 @@ class PPVectorPredictor:
         torch.cuda.current_stream().synchronize()
         return out
 
-    def extract_embeddings_stream(self, pinned_batches, input_lens_ratio=None):
-        """Pipelined form of extract_embeddings_pinned for a sequence of pinned [B,L] float32 host batches: the H2D
-        copy of batch i+1 runs on a copy stream while batch i is in the kernels (two device staging buffers, events
-        in both directions).  Yields one pinned host [B,embd] tensor per batch, in order; every batch still pays its
-        own H2D and D2H -- they are overlapped, not skipped."""
-        comp = torch.cuda.current_stream(self.device)
+    def _lanes(self, n):
+        """Compute lanes for the streaming calls.  Lane 0 is this predictor's model and featurizer; further lanes are replicas (same weights,
+        own workspace, own featurizer scratch) that run on their own CUDA streams, so that two batches can be in the kernels at once: the
+        persistent kernels of one batch leave SMs idle in their last tile round, between dependent launches and in the one-row-per-utterance
+        layers (2-6 CTAs), and the other batch's kernels take them."""
+        lanes = getattr(self, '_lane_objs', None)
+        if lanes is None:
+            lanes = self._lane_objs = [(self.predictor, self._audio_featurizer, None)]
+        while len(lanes) < n:
+            fz = AudioFeaturizer(feature_method=self.configs.preprocess_conf.feature_method,
+                                 method_args=self.configs.preprocess_conf.get('method_args', {}))
+            bb = build_model(input_size=fz.feature_dim, configs=self.configs)
+            bb.load_state_dict(self.predictor.state_dict())
+            bb = bb.eval().to(self.device)
+            lanes.append((bb, fz, torch.cuda.Stream(self.device)))
+        for bb, _, _ in lanes[1:n]:
+            if getattr(bb, 'precision', None) != getattr(self.predictor, 'precision', None):
+                bb.set_precision(self.predictor.precision)
+        return lanes[:n]
+
+    def embed_resident_stream(self, device_batches, input_lens_ratio=None, lanes=3):
+        """Device-resident [B,L] float32 waveform batches -> list of device [B,embd] embeddings (one per batch, in order), batches dealt round
+        robin to ``lanes`` compute lanes.  Returns after enqueueing; the caller's stream waits for every lane."""
+        main = torch.cuda.current_stream(self.device)
+        L = self._lanes(max(1, int(lanes)))
+        start = torch.cuda.Event()
+        start.record(main)
+        outs = []
+        for i, wav in enumerate(device_batches):
+            model, fz, st = L[i % len(L)]
+            if st is None:
+                outs.append(model.forward_wav(fz, wav, input_lens_ratio))
+            else:
+                if i < len(L):
+                    st.wait_event(start)  # inputs produced on the caller's stream
+                with torch.cuda.stream(st):
+                    outs.append(model.forward_wav(fz, wav, input_lens_ratio))
+        for _, _, st in L[1:]:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            main.wait_event(ev)
+        return outs
+
+    def extract_embeddings_stream(self, pinned_batches, input_lens_ratio=None, lanes=3):
+        """Pipelined form of extract_embeddings_pinned for a sequence of pinned [B,L] float32 host batches.  The H2D copy of a batch runs on
+        a copy stream while earlier batches are in the kernels; batches are dealt round robin to ``lanes`` compute lanes (see _lanes), and the
+        kernels of the next batch are enqueued BEFORE the host waits for the oldest batch's embeddings.  Yields one pinned host [B,embd]
+        tensor per batch, in order (valid until the next item is requested); every batch still pays its own H2D and D2H -- they are
+        overlapped, not skipped."""
+        from collections import deque
+        L = self._lanes(max(1, int(lanes)))
+        nl = len(L)
+        main = torch.cuda.current_stream(self.device)
+        streams = [main if st is None else st for _, _, st in L]
         copy = getattr(self, '_copy_stream', None)
         if copy is None:
             copy = self._copy_stream = torch.cuda.Stream(self.device)
-        dev = [None, None]
-        ready = [torch.cuda.Event(), torch.cuda.Event()]
-        free = [torch.cuda.Event(), torch.cuda.Event()]
-        done = [torch.cuda.Event(), torch.cuda.Event()]
-        outs = [None, None]
+        nb = nl + 1      # device staging buffers: the batches in the kernels plus the one being copied
+        ns = 2 * nl      # pinned outputs / completion events: a lane's next batch is enqueued while its previous result is still unread
+        dev = [None] * nb
+        ready = [torch.cuda.Event() for _ in range(nb)]
+        free = [torch.cuda.Event() for _ in range(nb)]
+        done = [torch.cuda.Event() for _ in range(ns)]
+        outs = [None] * ns
         it = iter(pinned_batches)
 
         def stage(i, host):
-            k = i & 1
+            k = i % nb
             with torch.cuda.stream(copy):
-                if i >= 2:
-                    copy.wait_event(free[k])  # the kernels of batch i-2 have consumed this buffer
+                if i >= nb:
+                    copy.wait_event(free[k])  # the kernels of batch i - nb have consumed this buffer
                 if dev[k] is None or dev[k].shape != host.shape:
                     dev[k] = torch.empty(host.shape, dtype=torch.float32, device=self.device)
                 dev[k].copy_(host, non_blocking=True)
                 ready[k].record(copy)
 
-        nxt = next(it, None)
-        if nxt is None:
-            return
-        stage(0, nxt)
+        def launch(i):
+            k, ln, sl = i % nb, i % nl, i % ns
+            model, fz, _ = L[ln]
+            st = streams[ln]
+            with torch.cuda.stream(st):
+                st.wait_event(ready[k])
+                emb = model.forward_wav(fz, dev[k], input_lens_ratio)
+                free[k].record(st)
+                if outs[sl] is None or outs[sl].shape != emb.shape:
+                    outs[sl] = torch.empty(emb.shape, dtype=torch.float32).pin_memory()
+                outs[sl].copy_(emb, non_blocking=True)
+                done[sl].record(st)
+
+        inflight = deque()
         i = 0
-        while nxt is not None:
-            k = i & 1
-            comp.wait_event(ready[k])
-            emb = self.predictor.forward_wav(self._audio_featurizer, dev[k], input_lens_ratio)
-            free[k].record(comp)
-            if outs[k] is None or outs[k].shape != emb.shape:
-                outs[k] = torch.empty(emb.shape, dtype=torch.float32).pin_memory()
-            outs[k].copy_(emb, non_blocking=True)
-            done[k].record(comp)
-            nxt = next(it, None)
-            if nxt is not None:
-                stage(i + 1, nxt)  # overlaps with the kernels just enqueued
-            done[k].synchronize()
-            yield outs[k]
+        nxt = next(it, None)
+        while nxt is not None and len(inflight) < nl:
+            stage(i, nxt)
+            launch(i)
+            inflight.append(i)
             i += 1
+            nxt = next(it, None)
+        while inflight:
+            j = inflight.popleft()
+            if nxt is not None:  # keep the lanes fed before blocking on the oldest batch
+                stage(i, nxt)
+                launch(i)
+                inflight.append(i)
+                i += 1
+                nxt = next(it, None)
+            done[j % ns].synchronize()
+            yield outs[j % ns]
 
     def predict(self, audio_data, sample_rate=16000):
         """reference: predict.py:218-233 -> [embd] numpy"""

@@ -154,8 +154,6 @@ class PPVectorTrainer(object):
             raise NotImplementedError(f'training on the B200 path is implemented for EcapaTdnn (got {use_model}); no fallback')
         if cf.loss_conf.get('loss', 'AAMLoss') not in ('AAMLoss', 'AMLoss', 'ARMLoss', 'CELoss') or cf.optimizer_conf.get('optimizer', 'Adam') != 'Adam':
             raise NotImplementedError('training on the B200 path implements AAMLoss / AMLoss / ARMLoss / CELoss + Adam (configs/ecapa_tdnn.yml)')
-        if cf.train_conf.get('enable_amp', False):
-            raise NotImplementedError('enable_amp: the B200 training step runs its fp32-grade split-bf16 path only')
         if cf.dataset_conf.get('is_use_pksampler', False):
             raise NotImplementedError('PKSampler is out of scope of the B200 path')
         torch.manual_seed(1000)  # trainer.py:290
@@ -181,6 +179,11 @@ class PPVectorTrainer(object):
                        if k in model_args}
         engine = TrainEngine(input_size=fz.feature_dim, num_speakers=num_speakers, embd_dim=model_args.get('embd_dim', 192), device=self.device,
                              **engine_args)
+        if cf.train_conf.get('enable_amp', False):
+            # reference trainer.py:167, 209-229: auto_cast(level='O1') + GradScaler(1024).  Here: single-pass bf16 GEMM operands, everything else
+            # fp32; bf16 has fp32's exponent range, so no loss scaling (nothing to unscale, no skipped steps)
+            engine.set_precision('bf16')
+            logger.info('enable_amp: bf16 operands in every GEMM of the step, fp32 accumulation / BatchNorm / loss / master weights')
         shapes = {k: tuple(v.shape) for k, v in backbone.state_dict().items()}
         sd = {k: v for k, v in backbone.state_dict().items()}
         cls_w = torch.empty(engine.embd_dim, num_speakers)
