@@ -311,6 +311,13 @@ int ppv_row_argmax(const float* sim, int rows, int cols, int32_t* idx, float* be
 #define PPV_HEAD_AM 2
 #define PPV_HEAD_ARM 3
 #define PPV_HEAD_CE 4
+/* SubCenterLoss (ppvector/loss/subcenterloss.py:33-54) with K sub-centres per class: pass PPV_HEAD_SUBCENTER | (K << 5) [| 1 for easy_margin];
+ * W / logits then have num_classes * K columns (fc.py:33: class c owns columns c*K .. c*K+K-1), a class's cosine is the max over its K. */
+#define PPV_HEAD_SUBCENTER 16
+/* SphereFace2 (ppvector/loss/sphereface2.py:44-70), a per-entry binary logistic loss, not a softmax: pass PPV_HEAD_SPHEREFACE2 | (t << 5)
+ * [| 1 for margin_type 'A'; default 'C'], the `label_smoothing` argument carries lanbuda (the positive / negative weight); the loss's
+ * bias stays at its initial 0 as in the reference (it is not among the optimizer's parameters). */
+#define PPV_HEAD_SPHEREFACE2 8
 int ppv_aam_forward(const float* emb, const float* W, const int64_t* labels, int B, int D, int S, float margin,
                     float scale, int easy_margin, float label_smoothing, float* logits, float* loss,
                     void* ws, size_t ws_bytes, void* stream);

@@ -97,8 +97,26 @@ def margin_head_loss(logits: torch.Tensor, labels: torch.Tensor, kind: str, marg
       'AM'  ppvector/loss/amloss.py:18-24    predictions = scale * (logits - margin * onehot)
       'ARM' ppvector/loss/armloss.py:18-31   as AM, then entries below their row's target value are replaced by 0
       'CE'  ppvector/loss/celoss.py:16-18    predictions = logits
+      'SF2C<t>' / 'SF2A<t>'  ppvector/loss/sphereface2.py:44-70 (label_smoothing = lanbuda)
+      'SUB<K>' / 'SUB<K>e'  ppvector/loss/subcenterloss.py:33-54 with K sub-centres (e: easy_margin)
     all with CrossEntropyLoss(reduction='sum', label_smoothing) / batch size."""
     B = logits.shape[0]
+    if kind.startswith("SUB"):  # "SUB<K>[e]": SubCenterLoss (subcenterloss.py:40-54): max over the K adjacent sub-centre columns, then AAMLoss
+        K = int(kind[3:].rstrip("e"))
+        cosine = logits.reshape(B, logits.shape[1] // K, K).max(dim=2).values
+        return aam_loss(cosine, labels, margin=margin, scale=scale, easy_margin=kind.endswith("e"), label_smoothing=label_smoothing)
+    if kind.startswith("SF2"):  # "SF2C<t>" / "SF2A<t>": SphereFace2 (sphereface2.py:44-70); label_smoothing carries lanbuda; bias = 0
+        t, lam = int(kind[4:]), label_smoothing
+        g = lambda z: 2 * ((z + 1) / 2) ** t - 1  # noqa: E731
+        if kind[3] == "A":
+            p = aam_params(margin)
+            sin = torch.sqrt((1.0 - logits ** 2).clamp_min(0))
+            zp = scale * g(torch.where(logits > p["th"], logits * p["cos_m"] - sin * p["sin_m"], logits - p["mmm"]))
+            zn = scale * g(logits * p["cos_m"] + sin * p["sin_m"])
+        else:
+            zp, zn = scale * (g(logits) - margin), scale * (g(logits) + margin)
+        tm = F.one_hot(labels, logits.shape[1]).to(logits.dtype)
+        return (tm * lam * F.softplus(-zp) + (1 - tm) * (1 - lam) * F.softplus(zn)).sum(1).mean()
     if kind == "CE":
         pred = logits
     else:

@@ -26,6 +26,8 @@ from ppvector.loss.aamloss import AAMLoss  # noqa: E402  (the REFERENCE's files 
 from ppvector.loss.amloss import AMLoss  # noqa: E402
 from ppvector.loss.armloss import ARMLoss  # noqa: E402
 from ppvector.loss.celoss import CELoss  # noqa: E402
+from ppvector.loss.sphereface2 import SphereFace2  # noqa: E402
+from ppvector.loss.subcenterloss import SubCenterLoss  # noqa: E402
 from ppvector.models.campplus import CAMPPlus  # noqa: E402
 from ppvector.models.ecapa_tdnn import EcapaTdnn  # noqa: E402
 from ppvector.models.eres2net import ERes2Net  # noqa: E402
@@ -188,6 +190,31 @@ def head_fixture():
         d[f"loss_{name}"] = np.array(float(loss))
         d[f"demb_{name}"] = e.grad.numpy()
         d[f"dW_{name}"] = clf.weight.grad.detach().numpy().copy()
+    # SubCenterLoss (subcenterloss.py) over a classifier with K sub-centres per class (fc.py:33): the first 156 columns of W as 52 x 3 / 78 x 2
+    for K, margin, ls, easy in [(3, 0.2, 0.0, False), (3, 0.3, 0.1, False), (2, 0.2, 0.0, True)]:
+        Sk = 156 // K
+        clfk = SpeakerIdentification(input_dim=D, num_speakers=Sk, K=K)
+        clfk.set_state_dict({"weight": Wc[:, :156].clone()})
+        lab = labels % Sk
+        e = paddle.to_tensor(emb)
+        e.requires_grad_(True)
+        loss = SubCenterLoss(margin=margin, scale=32, easy_margin=easy, K=K, label_smoothing=ls)(clfk(e), paddle.to_tensor(lab))
+        loss.backward()
+        tag = f"SUB_K{K}_m{margin}_ls{ls}_easy{int(easy)}"
+        d[f"loss_{tag}"] = np.array(float(loss))
+        d[f"demb_{tag}"] = e.grad.numpy()
+        d[f"dW_{tag}"] = clfk.weight.grad.detach().numpy().copy()
+    # SphereFace2 (sphereface2.py): both margin types
+    for mt, margin, lam, t in [("C", 0.2, 0.7, 3), ("A", 0.15, 0.7, 3), ("C", 0.3, 0.5, 2)]:
+        e = paddle.to_tensor(emb)
+        e.requires_grad_(True)
+        clf.weight.grad = None
+        loss = SphereFace2(margin=margin, scale=32.0, lanbuda=lam, t=t, margin_type=mt)(clf(e), paddle.to_tensor(labels))
+        loss.backward()
+        tag = f"SF2{mt}_m{margin}_l{lam}_t{t}"
+        d[f"loss_{tag}"] = np.array(float(loss))
+        d[f"demb_{tag}"] = e.grad.numpy()
+        d[f"dW_{tag}"] = clf.weight.grad.detach().numpy().copy()
     # AAMLoss.update (aamloss.py:48-53) == constructing with that margin
     crit = AAMLoss(margin=0.0, scale=32)
     crit.update(margin=0.25)

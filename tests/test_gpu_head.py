@@ -118,3 +118,48 @@ def test_other_softmax_heads_match_the_reference_code(cuda, golden_dir, kind, ma
         want = torch.from_numpy(want)
         rel = (got.double().cpu() - want).norm() / want.norm()
         assert rel < 5e-5, (tag, rel)
+
+
+@pytest.mark.parametrize("K,margin,ls,easy", [(3, 0.2, 0.0, False), (3, 0.3, 0.1, False), (2, 0.2, 0.0, True)])
+def test_subcenter_loss_matches_the_reference_code(cuda, golden_dir, K, margin, ls, easy):
+    """SubCenterLoss (ppvector/loss/subcenterloss.py:33-54; classifier with K sub-centres per class, fc.py:33) on the fused CUDA head against
+    the REFERENCE's own class (tests/golden/ref_head.npz): a class's cosine is the max over its K adjacent columns, the AAM margin rule on top,
+    and only the winning sub-centre column receives the class's gradient."""
+    from ppvector.loss import SubCenterLoss
+    from ppvector.models.fc import SpeakerIdentification
+    g = np.load(f"{golden_dir}/ref_head.npz")
+    Sk = 156 // K
+    emb = torch.from_numpy(g["emb"]).float().to(cuda).requires_grad_(True)
+    clf = SpeakerIdentification(input_dim=192, num_speakers=Sk, K=K).to(cuda)
+    with torch.no_grad():
+        clf.weight.copy_(torch.from_numpy(g["W"][:, :156].copy()).float())
+    crit = SubCenterLoss(margin=margin, scale=32, easy_margin=easy, K=K, label_smoothing=ls)
+    loss = crit(clf(emb), (torch.from_numpy(g["labels"]) % Sk).to(cuda))
+    loss.backward()
+    tag = f"SUB_K{K}_m{margin}_ls{ls}_easy{int(easy)}"
+    assert abs(loss.item() - float(g[f"loss_{tag}"])) < 2e-5 * max(1.0, abs(float(g[f"loss_{tag}"])))
+    for got, want in ((emb.grad, g[f"demb_{tag}"]), (clf.weight.grad, g[f"dW_{tag}"])):
+        want = torch.from_numpy(want)
+        rel = (got.double().cpu() - want).norm() / want.norm()
+        assert rel < 5e-5, (tag, rel)
+
+
+@pytest.mark.parametrize("mt,margin,lam,t", [("C", 0.2, 0.7, 3), ("A", 0.15, 0.7, 3), ("C", 0.3, 0.5, 2)])
+def test_sphereface2_matches_the_reference_code(cuda, golden_dir, mt, margin, lam, t):
+    """SphereFace2 (ppvector/loss/sphereface2.py:44-70: per-entry binary logistic loss over g(z) = 2 ((z+1)/2)^t - 1, margin types 'C' and 'A')
+    on the fused CUDA head against the REFERENCE's own class (tests/golden/ref_head.npz): loss and both gradients."""
+    from ppvector.loss import SphereFace2
+    from ppvector.models.fc import SpeakerIdentification
+    g = np.load(f"{golden_dir}/ref_head.npz")
+    emb = torch.from_numpy(g["emb"]).float().to(cuda).requires_grad_(True)
+    clf = SpeakerIdentification(input_dim=192, num_speakers=g["W"].shape[1]).to(cuda)
+    with torch.no_grad():
+        clf.weight.copy_(torch.from_numpy(g["W"]).float())
+    loss = SphereFace2(margin=margin, scale=32.0, lanbuda=lam, t=t, margin_type=mt)(clf(emb), torch.from_numpy(g["labels"]).to(cuda))
+    loss.backward()
+    tag = f"SF2{mt}_m{margin}_l{lam}_t{t}"
+    assert abs(loss.item() - float(g[f"loss_{tag}"])) < 2e-5 * max(1.0, abs(float(g[f"loss_{tag}"])))
+    for got, want in ((emb.grad, g[f"demb_{tag}"]), (clf.weight.grad, g[f"dW_{tag}"])):
+        want = torch.from_numpy(want)
+        rel = (got.double().cpu() - want).norm() / want.norm()
+        assert rel < 5e-5, (tag, rel)

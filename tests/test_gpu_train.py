@@ -200,3 +200,32 @@ def test_amp_bf16_operands_track_the_fp64_oracle(cuda, W64):
         got.append(li.item())
     print("amp bf16 loss curve", got, want)
     assert np.allclose(got, want, rtol=3e-2), (got, want)
+
+
+def test_subcenter_head_in_the_training_step(cuda, W64):
+    """loss_conf.loss = SubCenterLoss with model_conf.classifier.K = 3 (fc.py:33, subcenterloss.py:33-54): the step's classifier has S * K
+    columns and the head selector carries K.  The step's loss and classifier gradient must equal the standalone head (itself pinned to the
+    reference's class in test_gpu_head.py) applied to the step's own embeddings."""
+    from ppvector import _lib
+    from ppvector.loss import SubCenterLoss
+    K, B, T = 3, 4, 40
+    f, y, _ = make_problem(B, T, 77)
+    g = torch.Generator().manual_seed(5)
+    Wc = (torch.rand(192, S * K, generator=g, dtype=torch.float64) * 2 - 1) * (6.0 / (192 + S * K)) ** 0.5
+    eng = TrainEngine(input_size=80, num_speakers=S * K, device=cuda)
+    eng.load_state_dict(W64, Wc)
+    sel = _lib.PPV_HEAD_SUBCENTER | (K << 5)
+    loss, logits = eng.forward_backward(f.float().to(cuda), y.to(cuda), margin=0.2, scale=32.0, easy_margin=sel, return_logits=True)
+    torch.cuda.synchronize()
+    assert logits.shape == (B, S * K)
+    emb = eng.read_tap("emb", (B, 192)).clone().requires_grad_(True)
+    w = Wc.float().to(cuda).requires_grad_(True)
+    crit = SubCenterLoss(margin=0.2, scale=32, K=K)
+    cos = torch.nn.functional.normalize(emb) @ torch.nn.functional.normalize(w, dim=0)
+    assert (cos - logits).abs().max() < 1e-5
+    want = crit({"features": emb, "logits": cos, "_weight": w}, y.to(cuda))
+    want.backward()
+    assert abs(loss.item() - want.item()) < 1e-5 * max(1.0, abs(want.item()))
+    got_dw = eng.view("classifier.weight", (192, S * K), "grad")
+    rel = (got_dw - w.grad).norm() / w.grad.norm()
+    assert rel < 1e-4, rel

@@ -146,6 +146,27 @@ def test_head_and_aamloss_match_reference_code(golden_dir):
         assert abs(loss.item() - float(g[f"loss_{tag}"])) < 1e-10, tag
         close(e.grad.numpy(), g[f"demb_{tag}"])
         close(w.grad.numpy(), g[f"dW_{tag}"])
+    # SphereFace2 (loss/sphereface2.py)
+    for mt, margin, lam, t in [("C", 0.2, 0.7, 3), ("A", 0.15, 0.7, 3), ("C", 0.3, 0.5, 2)]:
+        e = torch.from_numpy(g["emb"]).requires_grad_(True)
+        w = torch.from_numpy(g["W"]).requires_grad_(True)
+        loss = head.margin_head_loss(head.cosine_logits(e, w), labels, f"SF2{mt}{t}", margin=margin, scale=32.0, label_smoothing=lam)
+        loss.backward()
+        tag = f"SF2{mt}_m{margin}_l{lam}_t{t}"
+        assert abs(loss.item() - float(g[f"loss_{tag}"])) < 1e-9 * max(1.0, abs(loss.item())), tag
+        close(e.grad.numpy(), g[f"demb_{tag}"])
+        close(w.grad.numpy(), g[f"dW_{tag}"])
+    # SubCenterLoss (loss/subcenterloss.py) over K sub-centres per class
+    for K, margin, ls, easy in [(3, 0.2, 0.0, False), (3, 0.3, 0.1, False), (2, 0.2, 0.0, True)]:
+        e = torch.from_numpy(g["emb"]).requires_grad_(True)
+        w = torch.from_numpy(g["W"][:, :156].copy()).requires_grad_(True)
+        loss = head.margin_head_loss(head.cosine_logits(e, w), labels % (156 // K), f"SUB{K}{'e' if easy else ''}", margin=margin, scale=32.0,
+                                     label_smoothing=ls)
+        loss.backward()
+        tag = f"SUB_K{K}_m{margin}_ls{ls}_easy{int(easy)}"
+        assert abs(loss.item() - float(g[f"loss_{tag}"])) < 1e-10, tag
+        close(e.grad.numpy(), g[f"demb_{tag}"])
+        close(w.grad.numpy(), g[f"dW_{tag}"])
 
 
 def test_train_step_matches_reference_code(golden_dir):

@@ -44,6 +44,7 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--precision", default="bf16x3")
     ap.add_argument("--once", default="")
+    ap.add_argument("--lanes", type=int, default=1, help="batches in flight: replica models on their own streams (see PPVectorPredictor._lanes)")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     names = [a.once] if a.once else a.models.split(",")
@@ -66,9 +67,45 @@ def main():
         torch.cuda.synchronize()
         ms = t0.elapsed_time(t1) / a.iters
         ws = _lib.load().ppv_model_workspace_bytes(m._get_handle(), a.batch, a.frames)
-        print(json.dumps({"model": name, "precision": a.precision, "batch": a.batch, "frames": a.frames, "ms_per_forward": round(ms, 3),
-                          "utt_per_s": round(a.batch / ms * 1e3, 1), "workspace_GB": round(ws / 2**30, 2),
-                          "finite": bool(torch.isfinite(e).all())}), flush=True)
+        line = {"model": name, "precision": a.precision, "batch": a.batch, "frames": a.frames, "ms_per_forward": round(ms, 3),
+                "utt_per_s": round(a.batch / ms * 1e3, 1), "workspace_GB": round(ws / 2**30, 2), "finite": bool(torch.isfinite(e).all())}
+        if a.lanes > 1:  # the same forwards dealt round robin to replica models on their own streams
+            reps = [m]
+            for _ in range(a.lanes - 1):
+                r = MODELS[name](input_size=80, precision=a.precision).eval()
+                r.load_state_dict(m.state_dict())
+                reps.append(r.to(dev))
+            streams = [torch.cuda.Stream(dev) for _ in reps]
+            main_s = torch.cuda.current_stream(dev)
+
+            def run(n):
+                ev = torch.cuda.Event()
+                ev.record(main_s)
+                outs = []
+                for i in range(n):
+                    st = streams[i % a.lanes]
+                    if i < a.lanes:
+                        st.wait_event(ev)
+                    with torch.cuda.stream(st):
+                        outs.append(reps[i % a.lanes](x))
+                for st in streams:
+                    d = torch.cuda.Event()
+                    d.record(st)
+                    main_s.wait_event(d)
+                return outs
+            outs = run(2 * a.lanes)
+            torch.cuda.synchronize()
+            same = all(torch.equal(o, e) for o in outs)
+            n = a.iters * a.lanes
+            t0.record()
+            run(n)
+            t1.record()
+            torch.cuda.synchronize()
+            msl = t0.elapsed_time(t1) / n
+            line.update({"lanes": a.lanes, "ms_per_forward_lanes": round(msl, 3), "utt_per_s_lanes": round(a.batch / msl * 1e3, 1),
+                         "bitwise_equal_to_one_lane": same})
+            del reps, outs
+        print(json.dumps(line), flush=True)
         del m, x
         torch.cuda.empty_cache()
 

@@ -130,25 +130,95 @@ __device__ __forceinline__ float block_reduce(float v, float* s_red, bool is_max
     return r;
 }
 
-// one block per row: loss_b and (optionally) G[b,s] = d loss / d cos[b,s]
+// SubCenterLoss (ppvector/loss/subcenterloss.py:40-43): the classifier holds K sub-centres per class in adjacent columns
+// (reshape(-1, S, K)); a class's cosine is the maximum over its K columns, and only that column receives the class's gradient.
+__device__ __forceinline__ float class_cosine(const float* __restrict__ c, int cls, int K, int* arg) {
+    float best = c[cls * K];
+    int a = 0;
+    for (int k = 1; k < K; ++k) {
+        const float v = c[cls * K + k];
+        if (v > best) {
+            best = v;
+            a = k;
+        }
+    }
+    *arg = a;
+    return best;
+}
+
+// SphereFace2 (ppvector/loss/sphereface2.py:44-70): NOT a softmax -- one binary logistic loss per (row, class) entry over
+// g(z) = 2 ((z + 1) / 2)^t - 1.  Type C: z_p = scale (g(c) - m), z_n = scale (g(c) + m); type A: g applied to the AAM-style shifted
+// cosines (cos(theta + m) with the same th / mmm fallback on the target, cos(theta - m) on the others).  Entry loss:
+// target lambda * log(1 + exp(-z_p)), others (1 - lambda) * log(1 + exp(z_n)); the loss's bias parameter is created at 0 and is not
+// handed to the optimizer in the reference (trainer.py:186-190 passes model.parameters() only), so it stays 0.
+__device__ __forceinline__ float sf2_entry(float c, bool is_target, bool type_a, int t, float lambda, float cos_m, float sin_m, float th,
+                                           float mmm, float margin, float scale, float* dl_dc) {
+    float inner = c, dinner = 1.f, shift = 0.f;
+    if (type_a) {
+        const float sine = sqrtf(fmaxf(1.f - c * c, 0.f));
+        const float ds = c / fmaxf(sine, 1e-6f);  // -d sine / dc
+        if (is_target) {
+            if (c > th) {
+                inner = c * cos_m - sine * sin_m;
+                dinner = cos_m + sin_m * ds;
+            } else {
+                inner = c - mmm;
+            }
+        } else {
+            inner = c * cos_m + sine * sin_m;
+            dinner = cos_m - sin_m * ds;
+        }
+    } else {
+        shift = is_target ? -margin : margin;
+    }
+    const float h = 0.5f * (inner + 1.f);
+    const float hp = powf(fmaxf(h, 0.f), float(t - 1));  // ((z + 1) / 2)^(t - 1)
+    const float g = 2.f * hp * h - 1.f;
+    const float dg = float(t) * hp * dinner;  // d g / d c
+    const float z = scale * (g + shift);
+    const float x = is_target ? -z : z;  // entry loss = w * softplus(x)
+    const float w = is_target ? lambda : 1.f - lambda;
+    const float sp = x > 20.f ? x : log1pf(expf(x));
+    const float sg = 1.f / (1.f + expf(-x));  // softplus'(x)
+    *dl_dc = w * sg * (is_target ? -1.f : 1.f) * scale * dg;
+    return w * sp;
+}
+
+// one block per row: loss_b and (optionally) G[b,s] = d loss / d cos[b,s].  S = classes, K = sub-centres per class (1: plain heads);
+// logits and G have S * K columns.
 __global__ void __launch_bounds__(256)
-    aam_row_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, int B, int S, float cos_m, float sin_m,
+    aam_row_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, int B, int S, int K, float cos_m, float sin_m,
                    float th, float mmm, int easy, float scale, float ls, float* __restrict__ row_loss, float* __restrict__ G, float margin) {
     __shared__ float s_red[8];
     const int b = blockIdx.x;
     const int64_t label = labels[b];
-    const float* c = logits + int64_t(b) * S;
-    const float zy = scale * (c[label] - margin);  // ARMLoss: the target's scaled logit is the threshold of its row
+    const float* c = logits + int64_t(b) * S * K;
+    if (easy & PPV_HEAD_SPHEREFACE2) {  // selector: PPV_HEAD_SPHEREFACE2 | type A bit | t << 5; `ls` carries lambda
+        const bool type_a = (easy & 1) != 0;
+        const int t = easy >> 5;
+        float acc = 0.f;
+        const float invB = 1.f / float(B);
+        for (int s = threadIdx.x; s < S; s += blockDim.x) {
+            float d;
+            acc += sf2_entry(c[s], s == label, type_a, t, ls, cos_m, sin_m, th, mmm, margin, scale, &d);
+            if (G) G[int64_t(b) * S + s] = d * invB;
+        }
+        acc = block_reduce(acc, s_red, false);
+        if (threadIdx.x == 0) row_loss[b] = acc;
+        return;
+    }
+    int arg;
+    const float zy = scale * (class_cosine(c, int(label), K, &arg) - margin);  // ARMLoss: the target's scaled logit is the threshold of its row
     float mx = -INFINITY;
     for (int s = threadIdx.x; s < S; s += blockDim.x) {
         float d;
-        mx = fmaxf(mx, head_value(c[s], s == label, easy, cos_m, sin_m, th, mmm, margin, scale, zy, &d));
+        mx = fmaxf(mx, head_value(class_cosine(c, s, K, &arg), s == label, easy, cos_m, sin_m, th, mmm, margin, scale, zy, &d));
     }
     mx = block_reduce(mx, s_red, true);
     float se = 0.f, so = 0.f, tgt = 0.f;
     for (int s = threadIdx.x; s < S; s += blockDim.x) {
         float d;
-        const float o = head_value(c[s], s == label, easy, cos_m, sin_m, th, mmm, margin, scale, zy, &d);
+        const float o = head_value(class_cosine(c, s, K, &arg), s == label, easy, cos_m, sin_m, th, mmm, margin, scale, zy, &d);
         se += expf(o - mx);
         so += o;
         if (s == label) tgt = o;
@@ -163,10 +233,10 @@ __global__ void __launch_bounds__(256)
         const float invB = 1.f / float(B);
         for (int s = threadIdx.x; s < S; s += blockDim.x) {
             float d;
-            const float o = head_value(c[s], s == label, easy, cos_m, sin_m, th, mmm, margin, scale, zy, &d);
+            const float o = head_value(class_cosine(c, s, K, &arg), s == label, easy, cos_m, sin_m, th, mmm, margin, scale, zy, &d);
             const float p = expf(o - lse);
             const float t = (s == label ? (1.f - ls) : 0.f) + ls / float(S);
-            G[int64_t(b) * S + s] = (p - t) * invB * d;
+            for (int k = 0; k < K; ++k) G[(int64_t(b) * S + s) * K + k] = k == arg ? (p - t) * invB * d : 0.f;
         }
     }
 }
@@ -176,6 +246,22 @@ __global__ void aam_mean_kernel(const float* __restrict__ row_loss, int B, float
         for (int b = 0; b < B; ++b) s += row_loss[b];  // fixed order: deterministic
         *loss = s / float(B);
     }
+}
+
+// head selector (the `easy_margin` argument of the ABI): 0-4 = PPV_HEAD_*; PPV_HEAD_SUBCENTER | (K << 5) | easy = SubCenterLoss with K sub-centres
+static int decode_head(int sel, int S, int* kind, int* K) {
+    *kind = sel;
+    *K = 1;
+    if (sel & PPV_HEAD_SUBCENTER) {
+        *K = sel >> 5;
+        *kind = sel & 1;
+        PPV_REQUIRE(*K >= 1 && S % *K == 0, "loss head: SubCenterLoss needs classifier columns = classes x K");
+    } else if (sel & PPV_HEAD_SPHEREFACE2) {
+        PPV_REQUIRE((sel >> 5) >= 1 && (sel >> 5) <= 16, "loss head: SphereFace2 needs 1 <= t <= 16 in the selector");
+    } else {
+        PPV_REQUIRE(sel >= 0 && sel <= PPV_HEAD_CE, "loss head: unknown selector");
+    }
+    return PPV_OK;
 }
 
 static void margin_consts(float margin, float* cos_m, float* sin_m, float* th, float* mmm) {
@@ -199,7 +285,10 @@ int aam_forward(const float* emb, const float* W, const int64_t* labels, int B, 
     PPV_LAUNCH_OK("aam_logits_kernel");
     float cm, sm, th, mmm;
     margin_consts(margin, &cm, &sm, &th, &mmm);
-    aam_row_kernel<<<B, 256, 0, st>>>(logits, labels, B, S, cm, sm, th, mmm, easy_margin, scale, label_smoothing, w.row_loss, nullptr, margin);
+    int kind, K;
+    int rc = decode_head(easy_margin, S, &kind, &K);
+    if (rc) return rc;
+    aam_row_kernel<<<B, 256, 0, st>>>(logits, labels, B, S / K, K, cm, sm, th, mmm, kind, scale, label_smoothing, w.row_loss, nullptr, margin);
     PPV_LAUNCH_OK("aam_row_kernel");
     aam_mean_kernel<<<1, 32, 0, st>>>(w.row_loss, B, loss);
     PPV_LAUNCH_OK("aam_mean_kernel");
@@ -264,7 +353,10 @@ int aam_backward(const float* emb, const float* W, const int64_t* labels, const 
     AamWs w = carve_aam(ws, B, D, S);  // e_hat / inv_e / inv_w are those of the forward call
     float cm, sm, th, mmm;
     margin_consts(margin, &cm, &sm, &th, &mmm);
-    aam_row_kernel<<<B, 256, 0, st>>>(logits, labels, B, S, cm, sm, th, mmm, easy_margin, scale, label_smoothing, w.row_loss, w.G, margin);
+    int kind, K;
+    int rc = decode_head(easy_margin, S, &kind, &K);
+    if (rc) return rc;
+    aam_row_kernel<<<B, 256, 0, st>>>(logits, labels, B, S / K, K, cm, sm, th, mmm, kind, scale, label_smoothing, w.row_loss, w.G, margin);
     PPV_LAUNCH_OK("aam_row_kernel(bwd)");
     const int64_t warps = int64_t(B) * D;
     aam_dehat_kernel<<<unsigned((warps + 7) / 8), 256, 0, st>>>(w.G, W, w.inv_w, B, D, S, w.dEh);

@@ -51,6 +51,8 @@ PPV_SPEC_SPECTROGRAM, PPV_SPEC_MEL, PPV_SPEC_LOGMEL, PPV_SPEC_MFCC = 1, 2, 3, 4
 PPV_SPECAUG_NPARAM = 16
 PPV_PREP_NI, PPV_PREP_NF = 8, 4
 PPV_HEAD_AAM, PPV_HEAD_AAM_EASY, PPV_HEAD_AM, PPV_HEAD_ARM, PPV_HEAD_CE = 0, 1, 2, 3, 4
+PPV_HEAD_SUBCENTER = 16  # | (K << 5) | easy_margin
+PPV_HEAD_SPHEREFACE2 = 8  # | (t << 5) | (margin_type == 'A'); lanbuda in the label_smoothing slot
 
 
 class SpectralCfg(C.Structure):

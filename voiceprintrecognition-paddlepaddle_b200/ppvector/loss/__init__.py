@@ -1,15 +1,16 @@
 """Loss factory keyed by ``loss_conf.loss`` (the reference's ppvector/loss/__init__.py:16-22 resolves the name by reflection over
-seven losses; this build implements AAMLoss -- the one every shipped config uses -- and AMLoss / ARMLoss / CELoss on the same fused CUDA
-head, and says so for the others)."""
+seven losses; this build implements AAMLoss -- the one every shipped config uses -- and AMLoss / ARMLoss / CELoss / SubCenterLoss / SphereFace2 on the
+same fused CUDA head, and says so for the others)."""
 from loguru import logger
 
 from .aamloss import AAMLoss
-from .margin_heads import AMLoss, ARMLoss, CELoss
+from .margin_heads import AMLoss, ARMLoss, CELoss, SphereFace2, SubCenterLoss
 
-__all__ = ['build_loss', 'AAMLoss', 'AMLoss', 'ARMLoss', 'CELoss']
+__all__ = ['build_loss', 'AAMLoss', 'AMLoss', 'ARMLoss', 'CELoss', 'SphereFace2', 'SubCenterLoss']
 
-_IMPLEMENTED = {'AAMLoss': AAMLoss, 'AMLoss': AMLoss, 'ARMLoss': ARMLoss, 'CELoss': CELoss}
-_REFERENCE_ONLY = ('SphereFace2', 'SubCenterLoss', 'TripletAngularMarginLoss')
+_IMPLEMENTED = {'AAMLoss': AAMLoss, 'AMLoss': AMLoss, 'ARMLoss': ARMLoss, 'CELoss': CELoss, 'SphereFace2': SphereFace2,
+                'SubCenterLoss': SubCenterLoss}
+_REFERENCE_ONLY = ('TripletAngularMarginLoss',)  # needs PK-sampled batches (equal positives per row: tripletangularmarginloss.py:57-58)
 
 
 def build_loss(configs):

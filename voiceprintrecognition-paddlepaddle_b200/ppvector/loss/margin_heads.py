@@ -6,6 +6,10 @@ the fly, online-softmax cross-entropy (``reduction='sum'`` / batch size = mean),
   AMLoss   z = scale * (cos - margin * onehot)
   ARMLoss  z as AMLoss, then every entry whose z is below its row's target z is replaced by 0
   CELoss   z = the logits as they are (no scale)
+  SphereFace2 (sphereface2.py:9-77)  not a softmax: lanbuda * softplus(-z_p) on the target entry, (1 - lanbuda) * softplus(z_n) on the others,
+           z over g(c) = 2 ((c + 1) / 2)^t - 1 with an additive ('C') or angular ('A') margin, summed over classes, mean over the batch
+  SubCenterLoss (subcenterloss.py:8-61)  the classifier has K sub-centres per class (fc.py:33: columns c*K .. c*K+K-1); a class's cosine
+           is the maximum over its K columns, then AAMLoss's margin rule; only the winning sub-centre receives the class's gradient
 """
 from torch import nn
 
@@ -37,6 +41,26 @@ class AMLoss(_MarginHead):
 
 class ARMLoss(_MarginHead):
     head = _lib.PPV_HEAD_ARM
+
+
+class SubCenterLoss(_MarginHead):
+    def __init__(self, margin=0.2, scale=32, easy_margin=False, K=3, label_smoothing=0.0):
+        super().__init__(margin=margin, scale=scale, label_smoothing=label_smoothing)
+        self.K = int(K)
+        self.head = _lib.PPV_HEAD_SUBCENTER | (self.K << 5) | int(bool(easy_margin))
+        self.easy_margin = self.head
+
+
+class SphereFace2(_MarginHead):
+    """sphereface2.py:9-77: per-entry binary logistic loss over g(z) = 2 ((z + 1) / 2)^t - 1; ``lanbuda`` weighs positives against negatives.
+    The reference creates a bias parameter at 0 and never hands it to the optimizer (trainer.py passes model.parameters() only): it is 0 here."""
+
+    def __init__(self, margin=0.2, scale=32.0, lanbuda=0.7, t=3, margin_type='C'):
+        super().__init__(margin=margin, scale=scale, label_smoothing=float(lanbuda))  # the ABI's label_smoothing slot carries lanbuda
+        assert margin_type in ('A', 'C') and 1 <= int(t) <= 16
+        self.lanbuda, self.t, self.margin_type = float(lanbuda), int(t), margin_type
+        self.head = _lib.PPV_HEAD_SPHEREFACE2 | (self.t << 5) | int(margin_type == 'A')
+        self.easy_margin = self.head
 
 
 class CELoss(_MarginHead):

@@ -126,22 +126,29 @@ class PPVectorPredictor:
 
     def embed_resident_stream(self, device_batches, input_lens_ratio=None, lanes=3):
         """Device-resident [B,L] float32 waveform batches -> list of device [B,embd] embeddings (one per batch, in order), batches dealt round
-        robin to ``lanes`` compute lanes.  Returns after enqueueing; the caller's stream waits for every lane."""
+        robin to ``lanes`` compute lanes.  The host keeps at most two batches queued per lane (it waits for the batch two turns back on the
+        same lane before enqueueing the next one), so the launch queues stay shallow; on return every batch has been enqueued and the
+        caller's stream waits for every lane."""
         main = torch.cuda.current_stream(self.device)
         L = self._lanes(max(1, int(lanes)))
+        nl = len(L)
+        streams = [main if st is None else st for _, _, st in L]
         start = torch.cuda.Event()
         start.record(main)
-        outs = []
+        outs, done = [], []
         for i, wav in enumerate(device_batches):
-            model, fz, st = L[i % len(L)]
-            if st is None:
-                outs.append(model.forward_wav(fz, wav, input_lens_ratio))
-            else:
-                if i < len(L):
+            model, fz, _ = L[i % nl]
+            st = streams[i % nl]
+            if i >= 2 * nl:
+                done[i - 2 * nl].synchronize()
+            with torch.cuda.stream(st):
+                if i < nl and st is not main:
                     st.wait_event(start)  # inputs produced on the caller's stream
-                with torch.cuda.stream(st):
-                    outs.append(model.forward_wav(fz, wav, input_lens_ratio))
-        for _, _, st in L[1:]:
+                outs.append(model.forward_wav(fz, wav, input_lens_ratio))
+                ev = torch.cuda.Event()
+                ev.record(st)
+                done.append(ev)
+        for st in streams[1:]:
             ev = torch.cuda.Event()
             ev.record(st)
             main.wait_event(ev)

@@ -152,8 +152,8 @@ class PPVectorTrainer(object):
         use_model = cf.model_conf.get('model', 'CAMPPlus')
         if use_model != 'EcapaTdnn':
             raise NotImplementedError(f'training on the B200 path is implemented for EcapaTdnn (got {use_model}); no fallback')
-        if cf.loss_conf.get('loss', 'AAMLoss') not in ('AAMLoss', 'AMLoss', 'ARMLoss', 'CELoss') or cf.optimizer_conf.get('optimizer', 'Adam') != 'Adam':
-            raise NotImplementedError('training on the B200 path implements AAMLoss / AMLoss / ARMLoss / CELoss + Adam (configs/ecapa_tdnn.yml)')
+        if cf.loss_conf.get('loss', 'AAMLoss') not in ('AAMLoss', 'AMLoss', 'ARMLoss', 'CELoss', 'SubCenterLoss', 'SphereFace2') or cf.optimizer_conf.get('optimizer', 'Adam') != 'Adam':
+            raise NotImplementedError('training on the B200 path implements AAMLoss / AMLoss / ARMLoss / CELoss / SubCenterLoss / SphereFace2 + Adam (configs/ecapa_tdnn.yml)')
         if cf.dataset_conf.get('is_use_pksampler', False):
             raise NotImplementedError('PKSampler is out of scope of the B200 path')
         torch.manual_seed(1000)  # trainer.py:290
@@ -173,8 +173,14 @@ class PPVectorTrainer(object):
         cls_conf = dict(cf.model_conf.get('classifier', {}))
         if model_args.get('pooling_type', 'ASP') != 'ASP' or not model_args.get('global_context', True):
             raise NotImplementedError('the B200 training step implements pooling_type="ASP" with global_context')
-        if cls_conf.get('classifier_type', 'Cosine') != 'Cosine' or int(cls_conf.get('K', 1)) != 1 or int(cls_conf.get('num_blocks', 0)) != 0:
-            raise NotImplementedError('the B200 training step implements classifier_type="Cosine", K=1, num_blocks=0')
+        if cls_conf.get('classifier_type', 'Cosine') != 'Cosine' or int(cls_conf.get('num_blocks', 0)) != 0:
+            raise NotImplementedError('the B200 training step implements classifier_type="Cosine", num_blocks=0')
+        cls_K = int(cls_conf.get('K', 1))  # fc.py:33: K sub-centres per class (SubCenterLoss); the classifier has num_speakers * K columns
+        loss_K = int((cf.loss_conf.get('loss_args', {}) or {}).get('K', 3)) if cf.loss_conf.get('loss', 'AAMLoss') == 'SubCenterLoss' else 1
+        if cls_K != loss_K:
+            raise ValueError(f'classifier K={cls_K} and loss K={loss_K} differ (SubCenterLoss needs model_conf.classifier.K == loss_args.K)')
+        num_classes = num_speakers
+        num_speakers = num_speakers * cls_K  # columns of the classifier from here on
         engine_args = {k: model_args[k] for k in ('channels', 'kernel_sizes', 'dilations', 'attention_channels', 'res2net_scale', 'se_channels')
                        if k in model_args}
         engine = TrainEngine(input_size=fz.feature_dim, num_speakers=num_speakers, embd_dim=model_args.get('embd_dim', 192), device=self.device,
@@ -255,6 +261,8 @@ class PPVectorTrainer(object):
                                                        easy_margin=criterion.easy_margin, label_smoothing=criterion.label_smoothing,
                                                        return_logits=True)
                 engine.adam_step(lr=scheduler.get_lr(), weight_decay=wd, grad_scale=engine.all_reduce_grads())
+                if cls_K > 1:  # trainer.py:231-234: a class's logit is the max over its sub-centres
+                    logits = logits.reshape(logits.shape[0], num_classes, cls_K).amax(2)
                 accs.append((logits.argmax(1).cpu() == label.cpu()).float().mean().item())
                 losses.append(float(loss))  # the reference syncs here too (trainer.py:237-238)
                 self.train_step += 1
