@@ -162,7 +162,9 @@ typedef struct {
 void ppv_resnetse_default_cfg(ppv_resnetse_cfg* cfg);
 
 /* kind PPV_MODEL_ERES2NET: ppvector/models/eres2net.py:239-263 (blocks :85-108, :147-170, AFF :46-52), TSTP head;
- * scale 2, expansion 2, base_width 32, one embedding layer (configs/eres2net.yml). */
+ * scale 2, expansion 2, base_width 32, one embedding layer (configs/eres2net.yml).  version = 2 selects ERes2NetV2
+ * (eres2net.py:266-462: the same blocks at base_width 26, i.e. chunk widths 13 / 26 / 52 / 104 zero-padded to 32 / 32 / 64 / 128 columns,
+ * AFF blocks in layers 3-4, `layer3_ds` + `fuse34` instead of the three-level bottom-up fusion; state_dict names as the reference's). */
 #define PPV_MODEL_ERES2NET 3
 typedef struct {
     int input_size;    /* 80 (must be a multiple of 8) */
@@ -170,6 +172,8 @@ typedef struct {
     int num_blocks[4]; /* 3,4,6,3 */
     int m_channels;    /* 32 (or 64) */
     int precision;     /* PPV_PREC_* */
+    int version;       /* 1 = ERes2Net (default; 0 means 1), 2 = ERes2NetV2 */
+    int base_width;    /* 32 for ERes2Net; ERes2NetV2: 26 (0 means the version's default) */
 } ppv_eres2net_cfg;
 void ppv_eres2net_default_cfg(ppv_eres2net_cfg* cfg);
 

@@ -12,6 +12,8 @@ Follows
   * ppvector/models/eres2net.py:147-170  BasicBlockERes2Net_diff_AFF.forward
   * ppvector/models/eres2net.py:239-263  ERes2Net.forward
   * ppvector/models/pooling.py:138-146   TemporalStatsPool (unbiased variance + 1e-8 under the sqrt)
+  * ppvector/models/eres2net.py:266-462  ERes2NetV2 (version=2: the same blocks at base_width 26 -- widths 13 / 26 / 52 / 104 --, AFF blocks in
+                                         layers 3-4, `layer3_ds` + `fuse34` instead of the three-level bottom-up fusion)
 """
 import math
 from typing import Dict
@@ -62,8 +64,9 @@ def block(x, W, prefix, stride, width, scale, fuse):
 
 
 def eres2net_forward(feats, W: Dict[str, torch.Tensor], num_blocks=(3, 4, 6, 3), m_channels=32, base_width=32, scale=2,
-                     taps=None):
-    """eres2net.py:239-263.  feats [B,T,F] -> [B,embd_dim]."""
+                     taps=None, version=1):
+    """eres2net.py:239-263 (version 1) / :440-462 (version 2: ERes2NetV2.forward, base_width 26, one bottom-up fusion of out3 into out4).
+    feats [B,T,F] -> [B,embd_dim]."""
     x = feats.transpose(1, 2).unsqueeze(1)
     out = F.relu(conv_bn(x, W, "conv1", "bn1", padding=1))
     outs = []
@@ -81,11 +84,16 @@ def eres2net_forward(feats, W: Dict[str, torch.Tensor], num_blocks=(3, 4, 6, 3),
     def ds(x, name):
         return F.conv2d(x, W[name + ".weight"], W[name + ".bias"], stride=2, padding=1)
 
-    f12 = aff(out2, ds(out1, "layer1_downsample"), W, "fuse_mode12")
-    f123 = aff(out3, ds(f12, "layer2_downsample"), W, "fuse_mode123")
-    f1234 = aff(out4, ds(f123, "layer3_downsample"), W, "fuse_mode1234")
-    if taps is not None:
-        taps["fuse12"], taps["fuse123"], taps["fuse1234"] = f12, f123, f1234
+    if version == 2:  # eres2net.py:452-453
+        f1234 = aff(out4, ds(out3, "layer3_ds"), W, "fuse34")
+        if taps is not None:
+            taps["fuse34"] = f1234
+    else:
+        f12 = aff(out2, ds(out1, "layer1_downsample"), W, "fuse_mode12")
+        f123 = aff(out3, ds(f12, "layer2_downsample"), W, "fuse_mode123")
+        f1234 = aff(out4, ds(f123, "layer3_downsample"), W, "fuse_mode1234")
+        if taps is not None:
+            taps["fuse12"], taps["fuse123"], taps["fuse1234"] = f12, f123, f1234
     mean = f1234.mean(dim=-1)
     std = torch.sqrt(f1234.var(dim=-1, unbiased=True) + 1e-8)
     stats = torch.cat((mean.flatten(1), std.flatten(1)), dim=1)
@@ -94,7 +102,7 @@ def eres2net_forward(feats, W: Dict[str, torch.Tensor], num_blocks=(3, 4, 6, 3),
     return stats @ W["seg_1.weight"] + W["seg_1.bias"]
 
 
-def eres2net_param_shapes(input_size=80, num_blocks=(3, 4, 6, 3), m_channels=32, expansion=2, base_width=32, scale=2, embd_dim=192):
+def eres2net_param_shapes(input_size=80, num_blocks=(3, 4, 6, 3), m_channels=32, expansion=2, base_width=32, scale=2, embd_dim=192, version=1):
     S = {}
 
     def conv(p, cin, cout, k):
@@ -135,12 +143,16 @@ def eres2net_param_shapes(input_size=80, num_blocks=(3, 4, 6, 3), m_channels=32,
                 conv(p + ".shortcut.0", in_planes, planes * expansion, 1)
                 bn(p + ".shortcut.1", planes * expansion)
             in_planes = planes * expansion
-    conv("layer1_downsample", m_channels * 2, m_channels * 4, 3)
-    conv("layer2_downsample", m_channels * 4, m_channels * 8, 3)
-    conv("layer3_downsample", m_channels * 8, m_channels * 16, 3)
-    aff_shapes("fuse_mode12", m_channels * 4)
-    aff_shapes("fuse_mode123", m_channels * 8)
-    aff_shapes("fuse_mode1234", m_channels * 16)
+    if version == 2:  # eres2net.py:403-406
+        conv("layer3_ds", m_channels * 8, m_channels * 16, 3)
+        aff_shapes("fuse34", m_channels * 16)
+    else:
+        conv("layer1_downsample", m_channels * 2, m_channels * 4, 3)
+        conv("layer2_downsample", m_channels * 4, m_channels * 8, 3)
+        conv("layer3_downsample", m_channels * 8, m_channels * 16, 3)
+        aff_shapes("fuse_mode12", m_channels * 4)
+        aff_shapes("fuse_mode123", m_channels * 8)
+        aff_shapes("fuse_mode1234", m_channels * 16)
     stats_dim = (input_size // 8) * m_channels * 8
     S["seg_1.weight"] = (stats_dim * expansion * 2, embd_dim)
     S["seg_1.bias"] = (embd_dim,)

@@ -30,7 +30,7 @@ from ppvector.loss.sphereface2 import SphereFace2  # noqa: E402
 from ppvector.loss.subcenterloss import SubCenterLoss  # noqa: E402
 from ppvector.models.campplus import CAMPPlus  # noqa: E402
 from ppvector.models.ecapa_tdnn import EcapaTdnn  # noqa: E402
-from ppvector.models.eres2net import ERes2Net  # noqa: E402
+from ppvector.models.eres2net import ERes2Net, ERes2NetV2  # noqa: E402
 from ppvector.models.fc import SpeakerIdentification  # noqa: E402
 from ppvector.models.resnet_se import ResNetSE  # noqa: E402
 from ppvector.optimizer.scheduler import MarginScheduler, cosine_decay_with_warmup  # noqa: E402
@@ -141,6 +141,13 @@ def models_fixture():
         d[f"eres2net_T{T}_emb"] = emb
         for k, v in taps.items():
             d[f"eres2net_T{T}_tap_{k}"] = v
+    # ---- ERes2NetV2 (eres2net.py:266-462): base_width 26 (widths 13 / 26 / 52 / 104), layer3_ds + fuse34
+    W = o_eres2net.make_eres2net_weights(seed=1000, dtype=torch.float64, base_width=26, version=2)
+    for T in (98, 298):
+        emb, taps = run(ERes2NetV2(input_size=80), W, feats("eres2net", T), ["layer1", "layer2", "layer3", "layer4", "fuse34", "pooling"])
+        d[f"eres2netv2_T{T}_emb"] = emb
+        for k, v in taps.items():
+            d[f"eres2netv2_T{T}_tap_{k}"] = v
     # ---- CAM++ (campplus.py:284-335); embd_dim 192 as configs/cam++.yml sets it
     W = o_campplus.make_campplus_weights(seed=1000, dtype=torch.float64)
     for T in (98, 298):

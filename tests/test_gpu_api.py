@@ -143,7 +143,7 @@ def test_trainer_extract_features_and_evaluate(cuda, wavs, cfg, W64, tmp_path):
     assert abs(min_dcf - float(compute_dcf(fnr, fpr))) < 1e-6
 
 
-@pytest.mark.parametrize("model_name", ["CAMPPlus", "ERes2Net", "ResNetSE"])
+@pytest.mark.parametrize("model_name", ["CAMPPlus", "ERes2Net", "ERes2NetV2", "ResNetSE"])
 def test_predictor_with_the_other_backbones(cuda, wavs, cfg, model_name):
     """PPVectorPredictor (predict.py:218-283) is model-agnostic in the reference: the same surface must drive every backbone."""
     import copy
@@ -152,10 +152,15 @@ def test_predictor_with_the_other_backbones(cuda, wavs, cfg, model_name):
     cfg = copy.deepcopy(cfg)
     cfg["model_conf"]["model"] = model_name
     cfg["model_conf"]["model_args"] = {"embd_dim": 192}
-    om = importlib.import_module({"CAMPPlus": "oracle.campplus", "ERes2Net": "oracle.eres2net", "ResNetSE": "oracle.resnet_se"}[model_name])
-    make = {"CAMPPlus": "make_campplus_weights", "ERes2Net": "make_eres2net_weights", "ResNetSE": "make_resnet_se_weights"}[model_name]
-    fwd = {"CAMPPlus": "campplus_forward", "ERes2Net": "eres2net_forward", "ResNetSE": "resnet_se_forward"}[model_name]
-    Wm = getattr(om, make)(seed=1000, dtype=torch.float64)
+    import functools
+    om = importlib.import_module({"CAMPPlus": "oracle.campplus", "ERes2Net": "oracle.eres2net", "ERes2NetV2": "oracle.eres2net",
+                                  "ResNetSE": "oracle.resnet_se"}[model_name])
+    make = {"CAMPPlus": "make_campplus_weights", "ERes2Net": "make_eres2net_weights", "ERes2NetV2": "make_eres2net_weights",
+            "ResNetSE": "make_resnet_se_weights"}[model_name]
+    fwd = {"CAMPPlus": "campplus_forward", "ERes2Net": "eres2net_forward", "ERes2NetV2": "eres2net_forward", "ResNetSE": "resnet_se_forward"}[model_name]
+    v2 = {"base_width": 26, "version": 2} if model_name == "ERes2NetV2" else {}
+    Wm = getattr(om, make)(seed=1000, dtype=torch.float64, **v2)
+    om = type("O", (), {fwd: staticmethod(functools.partial(getattr(om, fwd), **v2))})
     p = PPVectorPredictor(configs=cfg, state_dict={k: v.float().numpy() for k, v in Wm.items()})
     emb = p.predict(paths["a_2"])
     x = ofb.db_normalize(g["a_2_pcm"].astype(np.float32) / 32768.0, -20.0)

@@ -108,6 +108,18 @@ def test_eres2net_matches_reference_code(ref, T):
 
 
 @pytest.mark.parametrize("T", [98, 298])
+def test_eres2netv2_matches_reference_code(ref, T):
+    """ERes2NetV2 (eres2net.py:266-462): base_width 26 -> chunk widths 13 / 26 / 52 / 104, AFF blocks in layers 3-4, layer3_ds + fuse34"""
+    W = eres2net.make_eres2net_weights(seed=1000, dtype=torch.float64, base_width=26, version=2)
+    taps = {}
+    emb = eres2net.eres2net_forward(feats("eres2net", T), W, taps=taps, base_width=26, version=2)
+    close(emb.numpy(), ref[f"eres2netv2_T{T}_emb"])
+    for mine, theirs in [("layer1", "layer1"), ("layer2", "layer2"), ("layer3", "layer3"), ("layer4", "layer4"), ("fuse34", "fuse34"),
+                         ("stats", "pooling")]:
+        close(tap_slice(taps[mine]), ref[f"eres2netv2_T{T}_tap_{theirs}"])
+
+
+@pytest.mark.parametrize("T", [98, 298])
 def test_campplus_matches_reference_code(ref, T):
     W = campplus.make_campplus_weights(seed=1000, dtype=torch.float64)
     taps = {}

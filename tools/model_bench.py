@@ -15,10 +15,10 @@ sys.path.insert(0, os.path.join(ROOT, "voiceprintrecognition-paddlepaddle_b200")
 from ppvector import _lib  # noqa: E402
 from ppvector.models.campplus import CAMPPlus  # noqa: E402
 from ppvector.models.ecapa_tdnn import EcapaTdnn  # noqa: E402
-from ppvector.models.eres2net import ERes2Net  # noqa: E402
+from ppvector.models.eres2net import ERes2Net, ERes2NetV2  # noqa: E402
 from ppvector.models.resnet_se import ResNetSE  # noqa: E402
 
-MODELS = {"EcapaTdnn": EcapaTdnn, "ResNetSE": ResNetSE, "ERes2Net": ERes2Net, "CAMPPlus": CAMPPlus}
+MODELS = {"EcapaTdnn": EcapaTdnn, "ResNetSE": ResNetSE, "ERes2Net": ERes2Net, "ERes2NetV2": ERes2NetV2, "CAMPPlus": CAMPPlus}
 
 
 def randomize(m, seed=0):

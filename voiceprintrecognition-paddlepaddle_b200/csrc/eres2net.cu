@@ -31,6 +31,11 @@ struct EBlockW {
     GemmWeights conv1, sc, conv_a, conv_b, conv3, aff_a, aff_b;
     bool has_sc = false, fuse = false;
     int in_planes = 0, planes = 0, width = 0, wpad = 0, stride = 1, stage = 0;
+    // column plan of the conv1 output: chunk 0 at column 0, chunk 1 at column `c1_chunk1`; `c1_cols` columns in all.  Width 16 (ERes2Net
+    // layer 1) packs both chunks into one 32-column window; every other width gives each chunk its own `wpad`-column window (zero padded:
+    // ERes2NetV2's widths are 13 / 26 / 52 / 104).
+    int c1_chunk1 = 0, c1_cols = 0;
+    bool packed = false;
 };
 struct EFuseW {  // layerN_downsample + fuse_modeXYZ
     GemmWeights ds, aff_a, aff_b;
@@ -61,6 +66,7 @@ struct ERes2NetModel {
     std::vector<EBlockW> blocks;
     EFuseW fuse[3];
     GemmWeights seg1;
+    int fuse_first = 0;  // first bottom-up fusion stage in use (0: ERes2Net, 2: ERes2NetV2)
     int stats_ch = 0;  // 512 * F'
     // plan
     std::vector<EStep> steps;
@@ -81,6 +87,8 @@ void ppv_eres2net_default_cfg_impl(ppv_eres2net_cfg* c) {
     for (int i = 0; i < 4; ++i) c->num_blocks[i] = nb[i];
     c->m_channels = 32;
     c->precision = PPV_PREC_BF16X3;
+    c->version = 1;
+    c->base_width = 32;
 }
 
 int eres2net_create(const ppv_eres2net_cfg* cfg, ERes2NetModel** out) {
@@ -93,6 +101,9 @@ int eres2net_create(const ppv_eres2net_cfg* cfg, ERes2NetModel** out) {
     if (nblocks > ER_MAX_BLOCKS) return fail(PPV_EUNSUPPORTED, "eres2net: too many blocks");
     if (cfg->m_channels != 32 && cfg->m_channels != 64) return fail(PPV_EUNSUPPORTED, "eres2net: m_channels must be 32 or 64");
     if (cfg->input_size % 8 || cfg->embd_dim % 32) return fail(PPV_EUNSUPPORTED, "eres2net: input_size % 8, embd_dim % 32 required");
+    if (cfg->version != 0 && cfg->version != 1 && cfg->version != 2) return fail(PPV_EUNSUPPORTED, "eres2net: version must be 1 (ERes2Net) or 2 (ERes2NetV2)");
+    if (cfg->version != 2 && cfg->base_width != 0 && cfg->base_width != 32) return fail(PPV_EUNSUPPORTED, "eres2net: ERes2Net is built for base_width 32");
+    if (cfg->version == 2 && cfg->base_width != 0 && (cfg->base_width < 8 || cfg->base_width > 32)) return fail(PPV_EUNSUPPORTED, "eres2net: ERes2NetV2 base_width must be in [8, 32]");
     ERes2NetModel* m = new ERes2NetModel();
     m->cfg = *cfg;
     m->precision = cfg->precision;
@@ -131,9 +142,10 @@ int eres2net_finalize(ERes2NetModel* m) {
     struct KG {
         int taps, ncols, pos, cnt, cin0;
     };
-    // conv [N, Cin, k, k] (+ optional BN folded) -> dense [Npad][sum taps*ncols]
+    // conv [N, Cin, k, k] (+ optional BN folded) -> dense [Npad][sum taps*ncols]; output channel n lands in row n, or, with `chunk` > 0,
+    // in row (n / chunk) * chunk_stride + n % chunk (zero-padded output chunks)
     auto conv_matrix = [&](GemmWeights* gw, const std::string& conv, const std::string& bn, int N, int Npad, int Cin, int k,
-                           const std::vector<KG>& groups) {
+                           const std::vector<KG>& groups, int chunk = 0, int chunk_stride = 0) {
         const HostWeight* w = ab.get(conv + ".weight", {N, Cin, k, k});
         const HostWeight* b = ab.get(conv + ".bias", {N});
         std::vector<double> sc(N, 1.0), sh(N, 0.0);
@@ -147,15 +159,16 @@ int eres2net_finalize(ERes2NetModel* m) {
         std::vector<double> mtx(size_t(Npad) * K, 0.0);
         std::vector<float> bias(std::max(Npad, 64), 0.f);
         for (int n = 0; n < N; ++n) {
+            const int row = chunk > 0 ? (n / chunk) * chunk_stride + n % chunk : n;
             int kpos = 0;
             for (const KG& g : groups) {
                 for (int t = 0; t < g.taps; ++t) {
                     for (int c = 0; c < g.cnt; ++c)
-                        mtx[size_t(n) * K + kpos + t * g.ncols + g.pos + c] = double(w->v[(size_t(n) * Cin + g.cin0 + c) * taps + t]) * sc[n];
+                        mtx[size_t(row) * K + kpos + t * g.ncols + g.pos + c] = double(w->v[(size_t(n) * Cin + g.cin0 + c) * taps + t]) * sc[n];
                 }
                 kpos += g.taps * g.ncols;
             }
-            bias[n] = float(double(b->v[n]) * sc[n] + sh[n]);
+            bias[row] = float(double(b->v[n]) * sc[n] + sh[n]);
         }
         ab.put_matrix(gw, mtx, Npad, K);
         gw->N = Npad;
@@ -163,9 +176,9 @@ int eres2net_finalize(ERes2NetModel* m) {
     };
     auto aff_weights = [&](GemmWeights* ga, GemmWeights* gb, const std::string& p, int C, int src_cols) {
         // local_att.0: conv(2C -> C/4) over concat(x, y): two K groups of src_cols columns with C real channels each
-        const int inter = C / 4, ipad = std::max(inter, 32);
+        const int inter = C / 4, ipad = std::max((inter + 31) / 32 * 32, 32);
         conv_matrix(ga, p + ".local_att.0", p + ".local_att.1", inter, ipad, 2 * C, 1, {{1, src_cols, 0, C, 0}, {1, src_cols, 0, C, C}});
-        conv_matrix(gb, p + ".local_att.3", p + ".local_att.4", C, C, inter, 1, {{1, ipad, 0, inter, 0}});
+        conv_matrix(gb, p + ".local_att.3", p + ".local_att.4", C, (C + 31) / 32 * 32, inter, 1, {{1, ipad, 0, inter, 0}});
     };
     {  // stem: conv1 + bn1 folded
         const int C0 = cf.m_channels;
@@ -187,8 +200,10 @@ int eres2net_finalize(ERes2NetModel* m) {
     m->blocks.clear();
     m->blocks.reserve(ER_MAX_BLOCKS);  // arena patches point into the elements
     int in_planes = cf.m_channels;
+    const bool v2 = cf.version == 2;
+    const int base_width = v2 ? (cf.base_width > 0 ? cf.base_width : 26) : 32;
     for (int li = 1; li <= 4 && ok; ++li) {
-        const int planes = cf.m_channels << (li - 1), width = planes / 2, wpad = std::max(width, 32), C = 2 * planes;
+        const int planes = cf.m_channels << (li - 1), width = planes * base_width / 64, wpad = std::max((width + 31) / 32 * 32, 32), C = 2 * planes;
         for (int bi = 0; bi < cf.num_blocks[li - 1] && ok; ++bi) {
             m->blocks.emplace_back();
             EBlockW& bw = m->blocks.back();
@@ -199,16 +214,19 @@ int eres2net_finalize(ERes2NetModel* m) {
             bw.stage = li;
             bw.stride = (li > 1 && bi == 0) ? 2 : 1;
             bw.fuse = li >= 3;
+            bw.packed = (width == 16);
+            bw.c1_chunk1 = bw.packed ? width : wpad;
+            bw.c1_cols = bw.packed ? 32 : 2 * wpad;
             const std::string p = "layer" + std::to_string(li) + "." + std::to_string(bi);
-            conv_matrix(&bw.conv1, p + ".conv1", p + ".bn1", 2 * width, 2 * width, in_planes, 1, {{1, in_planes, 0, in_planes, 0}});
+            conv_matrix(&bw.conv1, p + ".conv1", p + ".bn1", 2 * width, bw.c1_cols, in_planes, 1, {{1, in_planes, 0, in_planes, 0}}, width, bw.c1_chunk1);
             // first 3x3: reads chunk 0 of the conv1 output (for width 16 the 32-wide window with the upper half zero-weighted)
             conv_matrix(&bw.conv_a, p + ".convs.0", p + ".bns.0", width, wpad, width, 3, {{9, wpad, 0, width, 0}});
             if (!bw.fuse) {
                 // second 3x3 on sp + spx[1]: K sources (sp buffer, conv1-output window holding chunk 1)
-                const int pos1 = (width >= 32) ? 0 : width;
+                const int pos1 = bw.packed ? width : 0;  // where chunk 1 sits inside the 32-column-aligned window the GEMM reads
                 conv_matrix(&bw.conv_b, p + ".convs.1", p + ".bns.1", width, wpad, width, 3, {{9, wpad, 0, width, 0}, {9, wpad, pos1, width, 0}});
             } else {
-                aff_weights(&bw.aff_a, &bw.aff_b, p + ".fuse_models.0", width, width);
+                aff_weights(&bw.aff_a, &bw.aff_b, p + ".fuse_models.0", width, wpad);
                 conv_matrix(&bw.conv_b, p + ".convs.1", p + ".bns.1", width, wpad, width, 3, {{9, wpad, 0, width, 0}});
             }
             conv_matrix(&bw.conv3, p + ".conv3", p + ".bn3", C, C, 2 * width, 1, {{1, wpad, 0, width, 0}, {1, wpad, 0, width, width}});
@@ -217,13 +235,15 @@ int eres2net_finalize(ERes2NetModel* m) {
             in_planes = C;
         }
     }
-    for (int i = 0; i < 3 && ok; ++i) {
+    // ERes2Net: three bottom-up fusions (eres2net.py:253-258); ERes2NetV2: only out3 -> out4 (layer3_ds + fuse34, eres2net.py:452-453)
+    m->fuse_first = v2 ? 2 : 0;
+    for (int i = m->fuse_first; i < 3 && ok; ++i) {
         const int Cin = cf.m_channels << (i + 1), Cout = 2 * Cin;  // layer(i+1)_downsample: 64->128, 128->256, 256->512
         EFuseW& fw = m->fuse[i];
         fw.C = Cout;
-        conv_matrix(&fw.ds, "layer" + std::to_string(i + 1) + "_downsample", "", Cout, Cout, Cin, 3, {{9, Cin, 0, Cin, 0}});
+        conv_matrix(&fw.ds, v2 ? std::string("layer3_ds") : "layer" + std::to_string(i + 1) + "_downsample", "", Cout, Cout, Cin, 3, {{9, Cin, 0, Cin, 0}});
         static const char* names[3] = {"fuse_mode12", "fuse_mode123", "fuse_mode1234"};
-        aff_weights(&fw.aff_a, &fw.aff_b, names[i], Cout, Cout);
+        aff_weights(&fw.aff_a, &fw.aff_b, v2 ? "fuse34" : names[i], Cout, Cout);
     }
     if (ok) {
         const int K = 2 * m->stats_ch, E = cf.embd_dim;
@@ -288,13 +308,13 @@ void er_carve(const ERes2NetModel* m, WsCarver& cv, int B, int T, ImageGeo* geo,
         const int64_t R = geo[st].rows(B);
         if (!have[st]) {
             have[st] = true;
-            s_c1[st] = cv.planes(R, 2 * bw.width);
+            s_c1[st] = cv.planes(R, bw.c1_cols);
             s_s0[st] = cv.planes(R, bw.wpad);
             s_s1[st] = cv.planes(R, bw.wpad);
             if (bw.fuse) {
-                s_a[st] = cv.planes(R, std::max(bw.width / 4, 32));
-                s_t[st] = cv.planes(R, bw.width);
-                s_xo[st] = cv.planes(R, bw.width);
+                s_a[st] = cv.planes(R, std::max((bw.width / 4 + 31) / 32 * 32, 32));
+                s_t[st] = cv.planes(R, bw.wpad);
+                s_xo[st] = cv.planes(R, bw.wpad);
             }
             s_o3[st] = cv.planes(R, 2 * bw.planes);
             s_act[st] = cv.planes(R, 2 * bw.planes);
@@ -311,7 +331,7 @@ void er_carve(const ERes2NetModel* m, WsCarver& cv, int B, int T, ImageGeo* geo,
         if (bw.has_sc) eb->sc[i] = s_act[st];
         eb->out[i] = s_act[st];
     }
-    for (int i = 0; i < 3; ++i) {
+    for (int i = m->fuse_first; i < 3; ++i) {
         const int64_t R = geo[i + 2].rows(B);
         const int C = m->fuse[i].C;
         eb->ds[i] = cv.planes(R, C);
@@ -463,9 +483,9 @@ static int er_build_plan(ERes2NetModel* m, int B, int T, void* ws, size_t ws_byt
         std::vector<GemmSource> tb;
         if (!bw.fuse) {
             taps9(eb.s0[i], 0, wp, go, &tb);
-            taps9(eb.c1[i], (w >= 32) ? w : 0, wp, go, &tb);
+            taps9(eb.c1[i], bw.packed ? 0 : bw.c1_chunk1, wp, go, &tb);
         } else {
-            rc = add_aff(bw.aff_a, bw.aff_b, eb.s0[i], 0, eb.c1[i], w, w, eb.a[i], eb.t[i], eb.xo[i], go);
+            rc = add_aff(bw.aff_a, bw.aff_b, eb.s0[i], 0, eb.c1[i], bw.c1_chunk1, wp, eb.a[i], eb.t[i], eb.xo[i], go);
             if (rc) return rc;
             taps9(eb.xo[i], 0, wp, go, &tb);
         }
@@ -493,8 +513,8 @@ static int er_build_plan(ERes2NetModel* m, int B, int T, void* ws, size_t ws_byt
         stage_out[bw.stage] = x;
     }
     // bottom-up fusion: fuse12 = AFF(out2, ds(out1)); fuse123 = AFF(out3, ds(fuse12)); fuse1234 = AFF(out4, ds(fuse123))
-    Planes prev = stage_out[1];
-    for (int i = 0; i < 3; ++i) {
+    Planes prev = stage_out[m->fuse_first + 1];
+    for (int i = m->fuse_first; i < 3; ++i) {
         const ImageGeo& gin = m->geo[i + 1];
         const ImageGeo& go = m->geo[i + 2];
         const EFuseW& fw = m->fuse[i];
@@ -527,7 +547,7 @@ static int er_build_plan(ERes2NetModel* m, int B, int T, void* ws, size_t ws_byt
     m->flat = eb.flat;
     m->stats = eb.stats;
     m->blk_out = eb.out;
-    for (int i = 0; i < 3; ++i) m->fuse_out[i] = eb.fout[i];
+    for (int i = m->fuse_first; i < 3; ++i) m->fuse_out[i] = eb.fout[i];
     m->emb_out = eb.emb_out;
     m->Tf = m->geo[4].W;
     m->plan_ws = ws;
@@ -593,8 +613,9 @@ int eres2net_read_tap(ERes2NetModel* m, const char* name, float* out, size_t out
             if (m->blocks[i].stage == stage) last = int(i);
         src = m->blk_out[last];
         C = 2 * (m->cfg.m_channels << (stage - 1));
-    } else if (n == "fuse12" || n == "fuse123" || n == "fuse1234") {
-        const int i = int(n.size()) - 6;
+    } else if (n == "fuse34" || n == "fuse12" || n == "fuse123" || n == "fuse1234") {
+        const int i = (n == "fuse34") ? 2 : int(n.size()) - 6;
+        PPV_REQUIRE(i >= m->fuse_first, "eres2net_read_tap: this fusion stage does not exist in ERes2NetV2");
         src = m->fuse_out[i];
         stage = i + 2;
         C = m->fuse[i].C;

@@ -43,7 +43,7 @@ PPV_MODEL_ERES2NET = 3
 
 class ERes2NetCfg(C.Structure):
     _fields_ = [("input_size", C.c_int), ("embd_dim", C.c_int), ("num_blocks", C.c_int * 4), ("m_channels", C.c_int),
-                ("precision", C.c_int)]
+                ("precision", C.c_int), ("version", C.c_int), ("base_width", C.c_int)]
 
 
 PPV_MODEL_CAMPPLUS = 4

@@ -4,14 +4,14 @@ from loguru import logger
 
 from .campplus import CAMPPlus
 from .ecapa_tdnn import EcapaTdnn
-from .eres2net import ERes2Net
+from .eres2net import ERes2Net, ERes2NetV2
 from .resnet_se import ResNetSE
 
-__all__ = ['build_model', 'CAMPPlus', 'EcapaTdnn', 'ERes2Net', 'ResNetSE']
+__all__ = ['build_model', 'CAMPPlus', 'EcapaTdnn', 'ERes2Net', 'ERes2NetV2', 'ResNetSE']
 
-_BACKBONES = {'CAMPPlus': CAMPPlus, 'EcapaTdnn': EcapaTdnn, 'ERes2Net': ERes2Net, 'ResNetSE': ResNetSE}
+_BACKBONES = {'CAMPPlus': CAMPPlus, 'EcapaTdnn': EcapaTdnn, 'ERes2Net': ERes2Net, 'ERes2NetV2': ERes2NetV2, 'ResNetSE': ResNetSE}
 # backbones the reference also ships; not part of the accelerated path
-_REFERENCE_ONLY = ('ERes2NetV2', 'Res2Net', 'TDNN')
+_REFERENCE_ONLY = ('Res2Net', 'TDNN')
 
 
 def build_model(input_size, configs):
