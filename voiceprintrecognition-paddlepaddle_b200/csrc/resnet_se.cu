@@ -78,57 +78,57 @@ struct ResNetSEModel {
 
 // ------------------------------------------------------------------------------------------------ small kernels
 // conv1: 1 -> C0 channels, 3x3, padding 1, BN folded, ReLU.  One thread per (output position, 8-channel group): the nine
-// inputs are read once per thread, weights come from shared memory, and each thread stores 16 bytes per plane so that a
-// warp writes whole 128-byte lines of consecutive positions.
+// inputs are read once per thread and each thread stores 16 bytes per plane so that a warp writes whole 128-byte lines of
+// consecutive positions.
 __global__ void __launch_bounds__(256)
     rs_conv1_kernel(const float* __restrict__ feat, int B, int T, int F, const float* __restrict__ w9, const float* __restrict__ bias, int C0,
                     Planes out, int Hp, int Wp) {
-    __shared__ float s_w[64 * 9];
-    __shared__ float s_b[64];
     griddep_launch_dependents();
-    for (int i = threadIdx.x; i < C0 * 9; i += 256) s_w[i] = w9[i];
-    for (int i = threadIdx.x; i < C0; i += 256) s_b[i] = bias[i];
-    __syncthreads();
-    griddep_wait();
+    // A thread owns one group of 8 output channels for the whole launch (the group count divides the block size): its 72 weights and 8
+    // biases live in registers, and it walks the positions with a grid stride.  (Per-position weight reads from shared memory made the
+    // kernel LDS-bound: 72 LDS for 72 FMAs.)
     const int groups = C0 >> 3;
-    const int64_t total = int64_t(B) * F * T * groups;
-    const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
-    if (i >= total) return;
-    const int g = int(i % groups);
-    const int64_t pos = i / groups;
-    const int b = int(pos / (int64_t(F) * T));
-    const int rem = int(pos - int64_t(b) * F * T);
-    const int h = rem / T, w = rem % T;  // h = frequency bin, w = frame
-    float x[9];
+    const int g = threadIdx.x % groups;
+    float wr[8][9], br[8];
 #pragma unroll
-    for (int dh = -1; dh <= 1; ++dh)
+    for (int c = 0; c < 8; ++c) {
+        br[c] = __ldg(bias + g * 8 + c);
 #pragma unroll
-        for (int dw = -1; dw <= 1; ++dw) {
-            const int hh = h + dh, ww = w + dw;
-            // input image is feats transposed: in[h][w] = feat[b][w][h]  (resnet_se.py:122-123)
-            x[(dh + 1) * 3 + dw + 1] = (hh >= 0 && hh < F && ww >= 0 && ww < T) ? __ldg(feat + (int64_t(b) * T + ww) * F + hh) : 0.f;
-        }
-    const int64_t row = (int64_t(b) * Hp + h + 1) * Wp + w + 1;
-    uint32_t hw[4], lw[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        float y[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int c = g * 8 + 2 * j + e;
-            float acc = s_b[c];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) acc = fmaf(s_w[c * 9 + k], x[k], acc);
-            y[e] = fmaxf(acc, 0.f);
-        }
-        __nv_bfloat16 h0, l0, h1, l1;
-        split_bf16(y[0], h0, l0);
-        split_bf16(y[1], h1, l1);
-        hw[j] = pack_bf16x2(h0, h1);
-        lw[j] = pack_bf16x2(l0, l1);
+        for (int k = 0; k < 9; ++k) wr[c][k] = __ldg(w9 + (g * 8 + c) * 9 + k);
     }
-    *reinterpret_cast<uint4*>(out.hi() + row * out.ld + g * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-    *reinterpret_cast<uint4*>(out.lo() + row * out.ld + g * 8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    griddep_wait();
+    const int64_t npos = int64_t(B) * F * T;
+    const int64_t pstep = int64_t(gridDim.x) * (256 / groups);
+    for (int64_t pos = int64_t(blockIdx.x) * (256 / groups) + threadIdx.x / groups; pos < npos; pos += pstep) {
+        const int b = int(pos / (int64_t(F) * T));
+        const int rem = int(pos - int64_t(b) * F * T);
+        const int h = rem / T, w = rem % T;  // h = frequency bin, w = frame
+        float x[9];
+#pragma unroll
+        for (int dh = -1; dh <= 1; ++dh)
+#pragma unroll
+            for (int dw = -1; dw <= 1; ++dw) {
+                const int hh = h + dh, ww = w + dw;
+                // input image is feats transposed: in[h][w] = feat[b][w][h]  (resnet_se.py:122-123)
+                x[(dh + 1) * 3 + dw + 1] = (hh >= 0 && hh < F && ww >= 0 && ww < T) ? __ldg(feat + (int64_t(b) * T + ww) * F + hh) : 0.f;
+            }
+        const int64_t row = (int64_t(b) * Hp + h + 1) * Wp + w + 1;
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float y[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                float acc = br[2 * j + e];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) acc = fmaf(wr[2 * j + e][k], x[k], acc);
+                y[e] = fmaxf(acc, 0.f);
+            }
+            split_pack_bf16x2(y[0], y[1], hw[j], lw[j]);
+        }
+        *reinterpret_cast<uint4*>(out.hi() + row * out.ld + g * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4*>(out.lo() + row * out.ld + g * 8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    }
 }
 
 // [B, Hp, Wp, C] image -> [B * W, C * H] time-major matrix with channel index c * H + h  (x.reshape([B, -1, T']),
@@ -164,10 +164,10 @@ __global__ void rs_image_to_f32_kernel(Planes in, int B, int H, int W, int Hp, i
 
 int launch_stem_conv(const float* feat, int B, int T, int F, const float* w9, const float* bias, int C0, const Planes& out, int Hp, int Wp,
                      cudaStream_t st) {
-    PPV_REQUIRE(C0 % 8 == 0 && C0 <= 64 && out.ld % 8 == 0, "stem conv: C0 % 8 == 0, C0 <= 64 required");
+    PPV_REQUIRE((C0 == 32 || C0 == 64) && out.ld % 8 == 0, "stem conv: C0 must be 32 or 64");
     const int64_t total = int64_t(B) * F * T * (C0 / 8);
-    PPV_PDL_OK(launch_pdl(rs_conv1_kernel, dim3(unsigned((total + 255) / 256)), dim3(256), 0, st, feat, B, T, F, w9, bias, C0, out, Hp, Wp),
-               "rs_conv1_kernel");
+    const unsigned grid = unsigned(std::min<int64_t>((total + 255) / 256, int64_t(device_sm_count()) * 8));
+    PPV_PDL_OK(launch_pdl(rs_conv1_kernel, dim3(grid), dim3(256), 0, st, feat, B, T, F, w9, bias, C0, out, Hp, Wp), "rs_conv1_kernel");
     return PPV_OK;
 }
 int launch_flatten_image(const Planes& in, int B, int H, int W, int Hp, int Wp, int C, const Planes& out, int num_sms, cudaStream_t st) {
