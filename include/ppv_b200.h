@@ -236,6 +236,11 @@ int ppv_model_profile_read(ppv_model_t* h, double* gemm_ms, double* other_ms, in
  * training is one all-reduce(sum) over the gradient buffer followed by ppv_adam_step(grad_scale = 1 / nranks)
  * (the reference's fleet.distributed_model, trainer.py:318-320).
  * ------------------------------------------------------------------------------------------- */
+/* Process-wide: 1 (default) = kernels are launched with programmatic dependent launch (the next kernel of a stream starts its prologue while
+ * the previous one drains), 0 = plain stream order.  Switch it off while several batches are in flight on different streams (see
+ * lanes): an early-launched dependent CTA occupies a whole SM while it waits.  Returns the previous setting. */
+int ppv_set_pdl(int enabled);
+
 typedef struct ppv_trainer ppv_trainer_t;
 int ppv_trainer_create(const ppv_ecapa_cfg* cfg, int num_classes, ppv_trainer_t** out);
 int ppv_trainer_destroy(ppv_trainer_t* h);

@@ -385,6 +385,11 @@ int ppv_trainer_lookup(const ppv_trainer_t* h, const char* name, int64_t* offset
     return trainer_lookup(h->impl, name, offset, numel, is_stat);
     PPV_GUARD_END
 }
+int ppv_set_pdl(int enabled) {
+    const int prev = ppv::pdl_enabled();
+    ppv::pdl_enabled() = enabled ? 1 : 0;
+    return prev;
+}
 int ppv_trainer_set_precision(ppv_trainer_t* h, int precision) {
     PPV_GUARD_BEGIN
     PPV_REQUIRE(h, "ppv_trainer_set_precision: null handle");

@@ -47,6 +47,15 @@ int fail(int code, const std::string& msg);
         }                                                            \
     } while (0)
 
+// Process-wide switch (ppv_set_pdl): 1 = launches carry the programmatic-stream-serialization attribute (default), 0 = plain stream order.
+// With SEVERAL batches in flight on different streams an early-launched dependent CTA sits on an SM (these kernels take a whole SM's shared
+// memory) until its primary grid has drained, and that SM is lost to the other streams' runnable kernels: callers that keep lanes busy
+// switch the early launch off for the duration (the kernels' griddepcontrol instructions are no-ops then).
+inline int& pdl_enabled() {
+    static int v = 1;
+    return v;
+}
+
 // Launch with programmatic dependent launch enabled (see ptx.cuh: griddep_wait / griddep_launch_dependents).
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
@@ -57,7 +66,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);

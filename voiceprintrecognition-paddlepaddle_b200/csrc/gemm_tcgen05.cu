@@ -550,7 +550,7 @@ static int launch_one(const GemmParams& gp, int num_sms, cudaStream_t stream) {
         cfg.stream = stream;
         cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
         attr[1].id = cudaLaunchAttributeClusterDimension;
         attr[1].val.clusterDim.x = 2;
         attr[1].val.clusterDim.y = 1;

@@ -110,6 +110,7 @@ SIGNATURES = {
     "ppv_trainer_lookup": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
     "ppv_trainer_bind": (C.c_int, [_P, _P, _P, _P]),
     "ppv_trainer_set_precision": (C.c_int, [_P, C.c_int]),
+    "ppv_set_pdl": (C.c_int, [C.c_int]),
     "ppv_trainer_workspace_bytes": (C.c_size_t, [_P, C.c_int, C.c_int]),
     "ppv_trainer_forward_backward": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, _P, _P, _P,
                                                C.c_size_t, _P]),

@@ -124,11 +124,24 @@ class PPVectorPredictor:
                 bb.set_precision(self.predictor.precision)
         return lanes[:n]
 
+    def _lanes_pdl(self, nl, restore=None):
+        """With more than one lane the kernels are launched WITHOUT programmatic dependent launch (ppv_set_pdl): an early-launched dependent
+        CTA holds a whole SM while its primary drains, which starves the other lanes' runnable kernels (measured: the multi-lane pass fell
+        into a slow mode in about half of the multi-process runs with it on).  PPV_LANES_PDL=1 keeps it on (A-B timing)."""
+        lib = _lib.load()
+        if restore is not None:
+            lib.ppv_set_pdl(restore)
+            return None
+        if nl > 1 and os.environ.get('PPV_LANES_PDL', '0') != '1':
+            return lib.ppv_set_pdl(0)
+        return None
+
     def embed_resident_stream(self, device_batches, input_lens_ratio=None, lanes=3):
         """Device-resident [B,L] float32 waveform batches -> list of device [B,embd] embeddings (one per batch, in order), batches dealt round
-        robin to ``lanes`` compute lanes.  The host keeps at most two batches queued per lane (it waits for the batch two turns back on the
-        same lane before enqueueing the next one), so the launch queues stay shallow; on return every batch has been enqueued and the
-        caller's stream waits for every lane."""
+        robin to ``lanes`` compute lanes.  The host enqueues a lane's next batch only when its previous one has finished (as
+        extract_embeddings_stream does): the launch queues stay shallow -- deep queues on several streams were measured to serialise badly
+        when other streams (NCCL's) share the device's hardware queues.  On return every batch has been enqueued and the caller's stream
+        waits for every lane."""
         main = torch.cuda.current_stream(self.device)
         L = self._lanes(max(1, int(lanes)))
         nl = len(L)
@@ -136,18 +149,23 @@ class PPVectorPredictor:
         start = torch.cuda.Event()
         start.record(main)
         outs, done = [], []
-        for i, wav in enumerate(device_batches):
-            model, fz, _ = L[i % nl]
-            st = streams[i % nl]
-            if i >= 2 * nl:
-                done[i - 2 * nl].synchronize()
-            with torch.cuda.stream(st):
-                if i < nl and st is not main:
-                    st.wait_event(start)  # inputs produced on the caller's stream
-                outs.append(model.forward_wav(fz, wav, input_lens_ratio))
-                ev = torch.cuda.Event()
-                ev.record(st)
-                done.append(ev)
+        pdl_prev = self._lanes_pdl(nl)
+        try:
+            for i, wav in enumerate(device_batches):
+                model, fz, _ = L[i % nl]
+                st = streams[i % nl]
+                if i >= nl:
+                    done[i - nl].synchronize()  # the lane is free again: at most `lanes` batches are queued on the device at any time
+                with torch.cuda.stream(st):
+                    if i < nl and st is not main:
+                        st.wait_event(start)  # inputs produced on the caller's stream
+                    outs.append(model.forward_wav(fz, wav, input_lens_ratio))
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                    done.append(ev)
+        finally:
+            if pdl_prev is not None:
+                self._lanes_pdl(nl, restore=pdl_prev)
         for st in streams[1:]:
             ev = torch.cuda.Event()
             ev.record(st)
@@ -200,12 +218,20 @@ class PPVectorPredictor:
                 outs[sl].copy_(emb, non_blocking=True)
                 done[sl].record(st)
 
+        def launch_no_pdl(i):  # see _lanes_pdl; the switch is process-wide, so it is flipped only around this generator's own launches
+            prev = self._lanes_pdl(nl)
+            try:
+                launch(i)
+            finally:
+                if prev is not None:
+                    self._lanes_pdl(nl, restore=prev)
+
         inflight = deque()
         i = 0
         nxt = next(it, None)
         while nxt is not None and len(inflight) < nl:
             stage(i, nxt)
-            launch(i)
+            launch_no_pdl(i)
             inflight.append(i)
             i += 1
             nxt = next(it, None)
@@ -213,7 +239,7 @@ class PPVectorPredictor:
             j = inflight.popleft()
             if nxt is not None:  # keep the lanes fed before blocking on the oldest batch
                 stage(i, nxt)
-                launch(i)
+                launch_no_pdl(i)
                 inflight.append(i)
                 i += 1
                 nxt = next(it, None)
