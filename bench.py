@@ -59,8 +59,8 @@ def synth_wave(batch, seed):
 
 
 class ClockSampler:
-    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md recipe), polled through NVML every ~2 ms in a
-    thread (an nvidia-smi subprocess at -lms 50 gets one sample into a 70 ms region); falls back to nvidia-smi -lms."""
+    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md recipe), polled through NVML every 50 ms in a
+    thread (in-process: an nvidia-smi subprocess needs ~100 ms before its first sample); falls back to nvidia-smi -lms."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -96,7 +96,7 @@ class ClockSampler:
                 self.power.append(n.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.05)  # B200_PROFILING.md samples at 200 ms; a 2 ms poll from a Python thread was measured to disturb the host-paced multi-lane pass
 
     def start(self):
         if self.nvml is not None:

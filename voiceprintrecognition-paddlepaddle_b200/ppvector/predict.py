@@ -125,23 +125,21 @@ class PPVectorPredictor:
         return lanes[:n]
 
     def _lanes_pdl(self, nl, restore=None):
-        """With more than one lane the kernels are launched WITHOUT programmatic dependent launch (ppv_set_pdl): an early-launched dependent
-        CTA holds a whole SM while its primary drains, which starves the other lanes' runnable kernels (measured: the multi-lane pass fell
-        into a slow mode in about half of the multi-process runs with it on).  PPV_LANES_PDL=1 keeps it on (A-B timing)."""
+        """PPV_LANES_PDL=0 launches the lanes' kernels WITHOUT programmatic dependent launch (ppv_set_pdl): an early-launched dependent CTA holds
+        a whole SM while its primary drains.  Measured either way without a consistent winner; the default keeps it on."""
         lib = _lib.load()
         if restore is not None:
             lib.ppv_set_pdl(restore)
             return None
-        if nl > 1 and os.environ.get('PPV_LANES_PDL', '0') != '1':
+        if nl > 1 and os.environ.get('PPV_LANES_PDL', '1') != '1':
             return lib.ppv_set_pdl(0)
         return None
 
     def embed_resident_stream(self, device_batches, input_lens_ratio=None, lanes=3):
         """Device-resident [B,L] float32 waveform batches -> list of device [B,embd] embeddings (one per batch, in order), batches dealt round
-        robin to ``lanes`` compute lanes.  The host enqueues a lane's next batch only when its previous one has finished (as
-        extract_embeddings_stream does): the launch queues stay shallow -- deep queues on several streams were measured to serialise badly
-        when other streams (NCCL's) share the device's hardware queues.  On return every batch has been enqueued and the caller's stream
-        waits for every lane."""
+        robin to ``lanes`` compute lanes, paced like extract_embeddings_stream: a lane's next batch is enqueued behind its running
+        one, then the host waits for the running one (lanes + 1 batches queued at most).  On return every batch has been enqueued and the
+        caller's stream waits for every lane."""
         main = torch.cuda.current_stream(self.device)
         L = self._lanes(max(1, int(lanes)))
         nl = len(L)
@@ -149,20 +147,27 @@ class PPVectorPredictor:
         start = torch.cuda.Event()
         start.record(main)
         outs, done = [], []
+        # PPV_LANES_STAGGER_MS (experiment, default off): delay lane k's first batch by k x this many ms so the lanes start out of phase; measured
+        # no better than starting together
+        stagger_cycles = int(float(os.environ.get('PPV_LANES_STAGGER_MS', '0')) * 1.9e6) if nl > 1 else 0
         pdl_prev = self._lanes_pdl(nl)
         try:
             for i, wav in enumerate(device_batches):
                 model, fz, _ = L[i % nl]
                 st = streams[i % nl]
-                if i >= nl:
-                    done[i - nl].synchronize()  # the lane is free again: at most `lanes` batches are queued on the device at any time
                 with torch.cuda.stream(st):
                     if i < nl and st is not main:
                         st.wait_event(start)  # inputs produced on the caller's stream
+                    if 0 < i < nl and stagger_cycles > 0:
+                        torch.cuda._sleep(i * stagger_cycles)  # see below: start the lanes out of phase
                     outs.append(model.forward_wav(fz, wav, input_lens_ratio))
                     ev = torch.cuda.Event()
                     ev.record(st)
                     done.append(ev)
+                if i >= nl:
+                    # as extract_embeddings_stream: the batch just enqueued sits BEHIND its lane's running one (the lane never drains), and the
+                    # host then waits for that running one -- at most lanes + 1 batches are queued on the device
+                    done[i - nl].synchronize()
         finally:
             if pdl_prev is not None:
                 self._lanes_pdl(nl, restore=pdl_prev)
