@@ -284,7 +284,8 @@ def main():
     # batch fill the SMs another batch leaves idle at its kernel tails and between dependent launches): the `value` of the line.
     for i in range(args.warmup):
         emb = model.forward_wav(fz, wavs[i % 2])
-    pred.embed_resident_stream((wavs[i % 2] for i in range(max(args.warmup, 2 * LANES))), lanes=LANES)
+    for _e in pred.embed_resident_stream((wavs[i % 2] for i in range(max(args.warmup, 2 * LANES))), lanes=LANES):
+        pass
     barrier()
     clocks = ClockSampler(local_rank)
     if rank == 0:
@@ -304,13 +305,15 @@ def main():
     assert torch.isfinite(emb).all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    embs = pred.embed_resident_stream((wavs[i % 2] for i in range(args.steps)), lanes=LANES)
+    last = None
+    for last in pred.embed_resident_stream((wavs[i % 2] for i in range(args.steps)), lanes=LANES):  # consumed and dropped: no allocator growth
+        pass
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
     clk = clocks.stop() if rank == 0 else None
-    assert all(torch.isfinite(e).all() for e in embs[-LANES:]) and torch.equal(embs[-1], emb)
-    del embs
+    assert torch.isfinite(last).all() and torch.equal(last, emb)  # the last batch of both passes is the same input: bitwise equal embeddings
+    del last
 
     # ---- end to end through the public API (host buffers) -----------------------------------------------------
     for out in pred.extract_embeddings_stream((host[i % 2] for i in range(2 * LANES)), lanes=LANES):

@@ -240,7 +240,8 @@ def test_streaming_lanes_equal_the_single_call(cuda, cfg, W64, lanes):
     for a, b in zip(got, want):
         assert np.array_equal(a, b)
     dev = [h.to(cuda) for h in host]
-    outs = pred.embed_resident_stream(dev, lanes=lanes)
-    torch.cuda.synchronize()
-    for a, b in zip(outs, want):
+    n = 0
+    for a, b in zip(pred.embed_resident_stream(dev, lanes=lanes), want):  # a generator: each embedding is complete when it is yielded
         assert np.array_equal(a.cpu().numpy(), b)
+        n += 1
+    assert n == len(want)

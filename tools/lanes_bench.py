@@ -27,14 +27,13 @@ def main():
     pred = PPVectorPredictor(cfg, model_path=None, use_gpu=True, state_dict=Wts)
     wavs = [bench.synth_wave(bench.BATCH, 1000 + i).to(dev) for i in range(2)]
     host = [bench.synth_wave(bench.BATCH, 2000 + i).pin_memory() for i in range(2)]
-    ref = pred.embed_resident_stream([wavs[0], wavs[1]], lanes=1)
+    ref = [e.clone() for e in pred.embed_resident_stream([wavs[0], wavs[1]], lanes=1)]
     for lanes in (1, 2, 3):
-        outs = pred.embed_resident_stream([wavs[i % 2] for i in range(6)], lanes=lanes)
-        torch.cuda.synchronize()
-        same = all(torch.equal(outs[i], ref[i % 2]) for i in range(6))
+        same = all(torch.equal(o, ref[i % 2]) for i, o in enumerate(pred.embed_resident_stream([wavs[i % 2] for i in range(6)], lanes=lanes)))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        pred.embed_resident_stream((wavs[i % 2] for i in range(a.steps)), lanes=lanes)
+        for _ in pred.embed_resident_stream((wavs[i % 2] for i in range(a.steps)), lanes=lanes):
+            pass
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / a.steps

@@ -136,46 +136,50 @@ class PPVectorPredictor:
         return None
 
     def embed_resident_stream(self, device_batches, input_lens_ratio=None, lanes=3):
-        """Device-resident [B,L] float32 waveform batches -> list of device [B,embd] embeddings (one per batch, in order), batches dealt round
-        robin to ``lanes`` compute lanes, paced like extract_embeddings_stream: a lane's next batch is enqueued behind its running
-        one, then the host waits for the running one (lanes + 1 batches queued at most).  On return every batch has been enqueued and the
-        caller's stream waits for every lane."""
+        """Generator: device-resident [B,L] float32 waveform batches -> one device [B,embd] embedding tensor per batch, in order, batches dealt
+        round robin to ``lanes`` compute lanes and paced like extract_embeddings_stream (a lane's next batch is enqueued behind its running
+        one, then the host waits for the oldest batch and yields it; lanes + 1 batches queued at most).  A yielded tensor is complete (the
+        host has synchronised on its lane) and stays valid for as long as the caller keeps it -- but a caller that keeps ALL of them makes
+        every step allocate fresh device memory, and cudaMalloc synchronises the whole device, which stalls every lane: consume and drop."""
+        from collections import deque
         main = torch.cuda.current_stream(self.device)
         L = self._lanes(max(1, int(lanes)))
         nl = len(L)
         streams = [main if st is None else st for _, _, st in L]
         start = torch.cuda.Event()
         start.record(main)
-        outs, done = [], []
         # PPV_LANES_STAGGER_MS (experiment, default off): delay lane k's first batch by k x this many ms so the lanes start out of phase; measured
         # no better than starting together (DESIGN.md 5a)
         stagger_cycles = int(float(os.environ.get('PPV_LANES_STAGGER_MS', '0')) * 1.9e6) if nl > 1 else 0
-        pdl_prev = self._lanes_pdl(nl)
-        try:
-            for i, wav in enumerate(device_batches):
-                model, fz, _ = L[i % nl]
-                st = streams[i % nl]
+        inflight = deque()  # (embedding, completion event), oldest first
+        for i, wav in enumerate(device_batches):
+            model, fz, _ = L[i % nl]
+            st = streams[i % nl]
+            pdl_prev = self._lanes_pdl(nl)
+            try:
                 with torch.cuda.stream(st):
                     if i < nl and st is not main:
                         st.wait_event(start)  # inputs produced on the caller's stream
                     if 0 < i < nl and stagger_cycles > 0:
-                        torch.cuda._sleep(i * stagger_cycles)  # see below: start the lanes out of phase
-                    outs.append(model.forward_wav(fz, wav, input_lens_ratio))
+                        torch.cuda._sleep(i * stagger_cycles)
+                    emb = model.forward_wav(fz, wav, input_lens_ratio)
                     ev = torch.cuda.Event()
                     ev.record(st)
-                    done.append(ev)
-                if i >= nl:
-                    # as extract_embeddings_stream: the batch just enqueued sits BEHIND its lane's running one (the lane never drains), and the
-                    # host then waits for that running one -- at most lanes + 1 batches are queued on the device
-                    done[i - nl].synchronize()
-        finally:
-            if pdl_prev is not None:
-                self._lanes_pdl(nl, restore=pdl_prev)
-        for st in streams[1:]:
-            ev = torch.cuda.Event()
-            ev.record(st)
-            main.wait_event(ev)
-        return outs
+            finally:
+                if pdl_prev is not None:
+                    self._lanes_pdl(nl, restore=pdl_prev)
+            inflight.append((emb, ev))
+            del emb
+            if len(inflight) > nl:
+                out, ev = inflight.popleft()
+                ev.synchronize()
+                yield out
+                del out
+        while inflight:
+            out, ev = inflight.popleft()
+            ev.synchronize()
+            yield out
+            del out
 
     def extract_embeddings_stream(self, pinned_batches, input_lens_ratio=None, lanes=3):
         """Pipelined form of extract_embeddings_pinned for a sequence of pinned [B,L] float32 host batches.  The H2D copy of a batch runs on
