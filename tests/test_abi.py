@@ -96,3 +96,48 @@ def test_every_shipped_config_builds_its_backbone():
         seen[cfg.model_conf.model] = sum(p.numel() for p in m.parameters())
     assert set(seen) == {"EcapaTdnn", "ResNetSE", "ERes2Net", "CAMPPlus"}
     assert seen["EcapaTdnn"] == 6194048 and seen["ERes2Net"] == 6620128 and seen["CAMPPlus"] == 6859232
+
+
+def test_loss_registry_and_head_selectors():
+    """loss/__init__.py:16-22 of the reference resolves seven loss classes by name; six run on the fused CUDA head here.  The head selector the
+    training loop forwards to the C ABI (include/ppv_b200.h: PPV_HEAD_*) is checked bit by bit; the seventh raises by name."""
+    from ppvector import _lib
+    from ppvector.loss import build_loss
+    from ppvector.utils.utils import dict_to_object
+
+    def mk(name, **args):
+        return build_loss(dict_to_object({"loss_conf": {"loss": name, "loss_args": args}}))
+
+    assert mk("AAMLoss", margin=0.2, scale=32).easy_margin in (0, False)
+    assert int(mk("AAMLoss", margin=0.2, scale=32, easy_margin=True).easy_margin) == _lib.PPV_HEAD_AAM_EASY
+    assert mk("AMLoss").easy_margin == _lib.PPV_HEAD_AM and mk("ARMLoss").easy_margin == _lib.PPV_HEAD_ARM
+    ce = mk("CELoss", label_smoothing=0.1)
+    assert ce.easy_margin == _lib.PPV_HEAD_CE and ce.scale == 1.0 and ce.label_smoothing == 0.1
+    sub = mk("SubCenterLoss", K=3, margin=0.3)
+    assert sub.easy_margin == (_lib.PPV_HEAD_SUBCENTER | (3 << 5)) and sub.margin == 0.3
+    assert mk("SubCenterLoss", K=2, easy_margin=True).easy_margin == (_lib.PPV_HEAD_SUBCENTER | (2 << 5) | 1)
+    sf = mk("SphereFace2", margin=0.15, lanbuda=0.6, t=3, margin_type="A")
+    assert sf.easy_margin == (_lib.PPV_HEAD_SPHEREFACE2 | (3 << 5) | 1) and sf.label_smoothing == 0.6  # lanbuda travels in that slot
+    assert mk("SphereFace2").easy_margin == (_lib.PPV_HEAD_SPHEREFACE2 | (3 << 5))
+    sub.update(margin=0.25)
+    assert sub.margin == 0.25
+    with pytest.raises(NotImplementedError, match="TripletAngularMarginLoss"):
+        mk("TripletAngularMarginLoss")
+    # the selectors do not collide: plain heads 0..4, SphereFace2 has bit 3, SubCenter bit 4, parameters from bit 5 up
+    assert _lib.PPV_HEAD_CE < _lib.PPV_HEAD_SPHEREFACE2 < _lib.PPV_HEAD_SUBCENTER < 32
+
+
+def test_eres2netv2_parameter_names_and_shapes():
+    """ERes2NetV2 (reference eres2net.py:379-438): the mirror's state_dict keys and shapes equal the reference class's (the oracle's shape table is
+    itself checked against the reference in tests/test_oracle_vs_reference.py by loading its weights into the reference model)."""
+    from oracle import eres2net as oe
+    from ppvector.models import build_model
+    from ppvector.utils.utils import dict_to_object
+    m = build_model(input_size=80, configs=dict_to_object({"model_conf": {"model": "ERes2NetV2", "model_args": {"embd_dim": 192}}}))
+    S = oe.eres2net_param_shapes(base_width=26, version=2)
+    sd = m.state_dict()
+    assert sorted(sd) == sorted(S)
+    for k, v in sd.items():
+        assert tuple(v.shape) == tuple(S[k]), k
+    assert "layer3_ds.weight" in sd and "fuse34.local_att.0.weight" in sd and "layer1_downsample.weight" not in sd
+    assert sd["layer1.0.convs.0.weight"].shape == (13, 13, 3, 3) and sd["layer4.0.convs.1.weight"].shape == (104, 104, 3, 3)
