@@ -148,9 +148,6 @@ class PPVectorPredictor:
         streams = [main if st is None else st for _, _, st in L]
         start = torch.cuda.Event()
         start.record(main)
-        # PPV_LANES_STAGGER_MS (experiment, default off): delay lane k's first batch by k x this many ms so the lanes start out of phase; measured
-        # no better than starting together
-        stagger_cycles = int(float(os.environ.get('PPV_LANES_STAGGER_MS', '0')) * 1.9e6) if nl > 1 else 0
         inflight = deque()  # (embedding, completion event), oldest first
         for i, wav in enumerate(device_batches):
             model, fz, _ = L[i % nl]
@@ -160,8 +157,6 @@ class PPVectorPredictor:
                 with torch.cuda.stream(st):
                     if i < nl and st is not main:
                         st.wait_event(start)  # inputs produced on the caller's stream
-                    if 0 < i < nl and stagger_cycles > 0:
-                        torch.cuda._sleep(i * stagger_cycles)
                     emb = model.forward_wav(fz, wav, input_lens_ratio)
                     ev = torch.cuda.Event()
                     ev.record(st)
