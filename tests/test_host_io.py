@@ -198,3 +198,45 @@ def test_wav_decoder_rejects_other_containers_by_name(tmp_path):
         fmt = struct.pack("<HHIIHH", 0x0055, 1, 16000, 2000, 1, 0)
         body = b"WAVE" + b"fmt " + struct.pack("<I", 16) + fmt + b"data" + struct.pack("<I", 4) + bytes(4)
         read_wav(b"RIFF" + struct.pack("<I", len(body)) + body)
+
+
+def _reference_windows(n, chunk_len, chunk_shift):
+    """the windowing rule of the reference written as its sequential loop (infer_utils/speaker_diarization.py:62-86): the spec for chunk_windows"""
+    out, last = [], 0
+    for st in range(0, n, chunk_shift):
+        ed = min(st + chunk_len, n)
+        if ed <= last:
+            break
+        last = ed
+        out.append((max(0, ed - chunk_len), ed))
+    return np.asarray(out, dtype=np.int64).reshape(-1, 2)
+
+
+def test_diarization_chunk_fan_out():
+    """1.5 s windows every 0.75 s over the voiced segments, the last window moved back to end at the segment end, short
+    segments zero-padded; every window goes to the embedding path as one equal-length batch (ppvector/infer_utils/chunking.py)."""
+    from ppvector.infer_utils.chunking import chunk_segments, chunk_windows, fan_out_embeddings
+    rng = np.random.default_rng(3)
+    for n in [0, 1, 11999, 12000, 23999, 24000, 24001, 36000, 64000, 64001, 100000] + list(rng.integers(1, 200000, size=40)):
+        assert np.array_equal(chunk_windows(int(n), 24000, 12000), _reference_windows(int(n), 24000, 12000)), n
+    assert np.array_equal(chunk_windows(50, 7, 3), _reference_windows(50, 7, 3))
+    # a 4.0 s segment starting at 2.0 s: four windows, the last one moved back to end at 6.0 s
+    x = rng.standard_normal(64000).astype(np.float32)
+    short = rng.standard_normal(8000).astype(np.float32)
+    times, chunks = chunk_segments([(2.0, 6.0, x), (7.5, 8.0, short)])
+    assert np.allclose(times, [[2.0, 3.5], [2.75, 4.25], [3.5, 5.0], [4.25, 5.75], [4.5, 6.0], [7.5, 8.0]])
+    assert chunks.shape == (6, 24000) and chunks.dtype == np.float32
+    assert np.array_equal(chunks[1], x[12000:36000]) and np.array_equal(chunks[4], x[40000:64000])
+    assert np.array_equal(chunks[5][:8000], short) and not chunks[5][8000:].any()
+    # fan-out: the embedding function sees equal-length batches of at most batch_size rows, results come back in window order
+    seen = []
+
+    def embed(b):
+        seen.append(b.shape)
+        return np.stack([b.mean(1), b.std(1)], axis=1)
+
+    t2, e = fan_out_embeddings([(2.0, 6.0, x), (7.5, 8.0, short)], embed, batch_size=4)
+    assert seen == [(4, 24000), (2, 24000)] and np.array_equal(t2, times)
+    assert np.allclose(e, np.stack([chunks.mean(1), chunks.std(1)], axis=1))
+    t0, e0 = fan_out_embeddings([], embed)
+    assert t0.shape == (0, 2) and e0.shape[0] == 0

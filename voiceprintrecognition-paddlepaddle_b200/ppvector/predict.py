@@ -270,6 +270,18 @@ class PPVectorPredictor:
         return np.concatenate([self.extract_embeddings(inputs[i:i + batch_size], ratio[i:i + batch_size])
                                for i in range(0, len(segs), batch_size)], axis=0)
 
+    def diarization_embeddings(self, audio_data, sample_rate=16000, vad_segments=None, seg_duration=1.5, seg_shift=0.75, batch_size=256):
+        """The embedding fan-out of the reference's ``speaker_diarization`` (predict.py:378-381): the recording (or the given voice-activity
+        segments [(start_s, end_s), ...]) is cut into ``seg_duration`` windows every ``seg_shift`` seconds (infer_utils/chunking.py) and every
+        window goes through the embedding path as ONE equal-length batch.  Returns (times [n, 2] seconds, embeddings [n, embd]).  VAD and the
+        clustering after it are outside the hot path: pass ``vad_segments`` from your VAD; None takes the whole recording as one segment."""
+        from ppvector.infer_utils.chunking import fan_out_embeddings
+        seg = self._load_audio(audio_data=audio_data, sample_rate=sample_rate)
+        sr, x = seg.sample_rate, seg.samples
+        spans = [(0.0, len(x) / sr)] if vad_segments is None else [(round(float(a), 3), round(float(b), 3)) for a, b in vad_segments]
+        segs = [(a, b, x[int(a * sr):int(b * sr)]) for a, b in spans]
+        return fan_out_embeddings(segs, self.extract_embeddings, seg_duration, seg_shift, sr, batch_size)
+
     def contrast(self, audio_data1, audio_data2):
         """reference: predict.py:271-283 -> cosine similarity of the two embeddings"""
         feature1 = self.predict(audio_data1)
