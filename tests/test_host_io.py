@@ -240,3 +240,30 @@ def test_diarization_chunk_fan_out():
     assert np.allclose(e, np.stack([chunks.mean(1), chunks.std(1)], axis=1))
     t0, e0 = fan_out_embeddings([], embed)
     assert t0.shape == (0, 2) and e0.shape[0] == 0
+
+
+def test_diarization_embeddings_wrapper_plumbing():
+    """PPVectorPredictor.diarization_embeddings = _load_audio (dB normalisation etc.) + the chunk fan-out + extract_embeddings.  The embedding call
+    needs the GPU; here it is stubbed to check what the wrapper hands to it (shapes, order, VAD spans, batch splitting)."""
+    import os
+
+    import yaml
+
+    from ppvector.predict import PPVectorPredictor
+    from ppvector.utils.utils import dict_to_object
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = PPVectorPredictor.__new__(PPVectorPredictor)  # no CUDA in this test: skip __init__
+    p.configs = dict_to_object(yaml.load(open(os.path.join(root, "configs", "ecapa_tdnn.yml")), Loader=yaml.FullLoader))
+    calls = []
+
+    def stub(w, ratio=None):
+        calls.append(w.shape)
+        return np.stack([w.mean(1), w.std(1)], 1).astype(np.float32)
+
+    p.extract_embeddings = stub
+    x = (0.1 * np.random.default_rng(5).standard_normal(80000)).astype(np.float32)
+    t, e = p.diarization_embeddings(x, sample_rate=16000, batch_size=4)
+    assert np.allclose(t, [[0, 1.5], [0.75, 2.25], [1.5, 3.0], [2.25, 3.75], [3.0, 4.5], [3.5, 5.0]]) and e.shape == (6, 2)
+    assert calls == [(4, 24000), (2, 24000)]
+    t2, e2 = p.diarization_embeddings(x, sample_rate=16000, vad_segments=[(0.5, 2.6), (3.0, 3.4)])
+    assert np.allclose(t2, [[0.5, 2.0], [1.1, 2.6], [3.0, 3.4]]) and e2.shape == (3, 2)
